@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the authoring container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The reference has no tests or golden vectors of its own,
+so these files ARE the pin: inputs (stored exactly, as bf16 bit patterns so the
+same numbers can be fed to reduced-precision kernels) and the outputs of the
+reference's own functions on them:
+  Objectives.xattn_score_t2i / xattn_score_i2t   (itr/modalmodule/Objectives.py:329-417)
+  Objectives.cosine_sim                           (:18-21)
+  Objectives.TripletLoss (+ torch autograd)       (:482-517; CPU-safe twin of ContrastiveLoss, defect D2)
+  evaluation.i2t / t2i                            (itr/metricmodule/evaluation.py:156-222)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+NORMS = ("clipped_l2norm", "l2norm", "softmax", "clipped", "no_norm")
+AGGS = ("LogSumExp", "Mean", "Max", "Sum")
+
+
+def bf16_bits(x: torch.Tensor) -> np.ndarray:
+    return x.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+def from_bits(b: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(b.view(np.int16).copy()).view(torch.bfloat16).to(torch.float32)
+
+
+def scan_case(O, name, n_img, lens, seed, d=1024, r=36):
+    g = torch.Generator().manual_seed(seed)
+    lens = np.asarray(lens, dtype=np.int32)
+    lmax = int(lens.max())
+    bank = torch.nn.functional.normalize(torch.randn(64, d, generator=g), dim=-1)
+    concept = torch.randint(0, 64, (n_img, r), generator=g)
+    images = torch.nn.functional.normalize(bank[concept] + 0.6 / d ** 0.5 * torch.randn(n_img, r, d, generator=g), dim=-1)
+    n_cap = len(lens)
+    caps = torch.zeros(n_cap, lmax, d)
+    for c in range(n_cap):
+        owner = c % n_img
+        pick = torch.randint(0, r, (int(lens[c]),), generator=g)
+        w = torch.nn.functional.normalize(bank[concept[owner, pick]] + 0.8 / d ** 0.5 * torch.randn(int(lens[c]), d, generator=g), dim=-1)
+        caps[c, :lens[c]] = (0.5 + 1.5 * torch.rand(int(lens[c]), 1, generator=g)) * w
+    img_bits, cap_bits = bf16_bits(images), bf16_bits(caps)
+    images, caps = from_bits(img_bits), from_bits(cap_bits)       # what everybody consumes
+    out = {"img_bits": img_bits, "cap_bits": cap_bits, "lens": lens}
+    for direction, fn, lam_sm in (("t2i", O.xattn_score_t2i, 9.0), ("i2t", O.xattn_score_i2t, 4.0)):
+        for norm in NORMS:
+            for agg in AGGS:
+                cfg = dict(raw_feature_norm=norm, agg_func=agg, lambda_lse=6.0, lambda_softmax=lam_sm)
+                with torch.no_grad():
+                    s32 = fn(images, caps, lens.tolist(), cfg).numpy()
+                    s64 = fn(images.double(), caps.double(), lens.tolist(), cfg).numpy()
+                out["{}|{}|{}|f32".format(direction, norm, agg)] = s32
+                out["{}|{}|{}|f64".format(direction, norm, agg)] = s64
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if "|" not in k})
+
+
+def main():
+    O, E = ref_loader.load()
+    torch.set_num_threads(8)
+    gold = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+
+    scan_case(O, "scan_small", n_img=8, lens=[16, 3, 12, 9, 5, 14, 7, 11, 16, 4, 13, 8], seed=101)
+    scan_case(O, "scan_long", n_img=5, lens=[72, 40, 33], seed=102)
+
+    # cosine + hinge
+    g = torch.Generator().manual_seed(103)
+    im = torch.nn.functional.normalize(torch.randn(24, 1024, generator=g), dim=-1)
+    s = torch.nn.functional.normalize(im + 0.9 / 32 * torch.randn(24, 1024, generator=g), dim=-1)
+    im_bits, s_bits = bf16_bits(im), bf16_bits(s)
+    im, s = from_bits(im_bits), from_bits(s_bits)
+    out = {"im_bits": im_bits, "s_bits": s_bits,
+           "cosine|f32": O.cosine_sim(im, s).numpy(), "cosine|f64": O.cosine_sim(im.double(), s.double()).numpy()}
+    for margin in (0.0, 0.2):
+        for mv in (False, True):
+            sc = O.cosine_sim(im.double(), s.double()).clone().requires_grad_(True)
+            loss = O.TripletLoss(margin=margin, max_violation=mv)(sc)
+            loss.backward()
+            key = "hinge|m{}|mv{}".format(margin, int(mv))
+            out[key + "|loss"] = np.float64(loss.item())
+            out[key + "|dscores"] = sc.grad.numpy()
+            # gradient w.r.t. the embeddings through the cosine similarity
+            a = im.double().clone().requires_grad_(True)
+            b = s.double().clone().requires_grad_(True)
+            O.TripletLoss(margin=margin, max_violation=mv)(O.cosine_sim(a, b)).backward()
+            out[key + "|d_im"] = a.grad.numpy()
+            out[key + "|d_s"] = b.grad.numpy()
+    np.savez_compressed(os.path.join(gold, "vse_hinge.npz"), **out)
+    print("vse_hinge", len(out))
+
+    # ranking
+    rng = np.random.default_rng(104)
+    n = 40
+    sims = rng.standard_normal((n, 5 * n))
+    sims[np.arange(n).repeat(5), np.arange(5 * n)] += 1.5          # make the ground truth competitive
+    (r, (ranks, top1)) = E.i2t(sims, return_ranks=True)
+    (ri, (ranks_i, top1_i)) = E.t2i(sims, return_ranks=True)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        rd = E.cal_recall(sims)
+    np.savez_compressed(os.path.join(gold, "ranking.npz"), sims=sims,
+                        i2t_metrics=np.asarray(r, dtype=np.float64), i2t_ranks=ranks, i2t_top1=top1,
+                        t2i_metrics=np.asarray(ri, dtype=np.float64), t2i_ranks=ranks_i, t2i_top1=top1_i,
+                        result=np.asarray(rd["result"], dtype=np.float64), rsum=np.float64(rd["rsum"]))
+    print("ranking", r, ri)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,47 @@
+"""Live check of the oracle against the unmodified reference, on fresh random
+inputs.  Only runs where /root/reference exists (the authoring container);
+skipped on the GPU box, where tests/golden is the pin."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader, scan_oracle as so
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
+@pytest.mark.parametrize("norm", so.RAW_FEATURE_NORMS)
+def test_scan_live(ref, direction, lam_sm, norm):
+    O, _ = ref
+    g = torch.Generator().manual_seed(7)
+    img = torch.nn.functional.normalize(torch.randn(5, 36, 96, generator=g, dtype=torch.float64), dim=-1)
+    lens = [11, 3, 7, 20, 1]
+    cap = torch.randn(5, 20, 96, generator=g, dtype=torch.float64)
+    for c, n in enumerate(lens):
+        cap[c, n:] = 0
+    fn = O.xattn_score_t2i if direction == "t2i" else O.xattn_score_i2t
+    for agg in so.AGG_FUNCS:
+        cfg = dict(raw_feature_norm=norm, agg_func=agg, lambda_lse=6.0, lambda_softmax=lam_sm)
+        # n_word == 1 collapses a dim in the reference's .squeeze() (defect D5): keep it out of the live call
+        use = [c for c, n in enumerate(lens) if n > 1]
+        want = fn(img, cap[use], [lens[c] for c in use], cfg).numpy()
+        got = so.scan_scores(img.numpy(), cap.numpy()[use], [lens[c] for c in use], direction, norm, agg, lam_sm, 6.0)
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+
+
+def test_rank_live(ref):
+    _, E = ref
+    rng = np.random.default_rng(3)
+    sims = rng.standard_normal((30, 150))
+    (r, (ranks, top1)) = E.i2t(sims, return_ranks=True)
+    m, a, b = so.rank_i2t(sims)
+    np.testing.assert_array_equal(a, ranks); np.testing.assert_array_equal(b, top1); np.testing.assert_allclose(m, r)
+    (r, (ranks, top1)) = E.t2i(sims, return_ranks=True)
+    m, a, b = so.rank_t2i(sims)
+    np.testing.assert_array_equal(a, ranks); np.testing.assert_array_equal(b, top1); np.testing.assert_allclose(m, r)
