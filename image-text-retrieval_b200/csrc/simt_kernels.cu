@@ -1,0 +1,731 @@
+// float32 CUDA-core kernels of libitr_b200: the 1e-5 "fp32 mode" of the hot path.
+//   - cosine scores / small dense products      (Objectives.py:18-21)
+//   - SCAN cross-attention scores, every mode   (Objectives.py:329-476)
+//   - max-violation / sum hinge, fwd + bwd      (Objectives.py:93-115, 492-517)
+//   - i2t / t2i rank counting                   (evaluation.py:156-222)
+// The throughput path for SCAN t2i lives in scan_t2i_tc.cu (tcgen05).
+#include <cfloat>
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace itr {
+
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+// =========================================================================================
+// Generic strided SGEMM:  C[m][n] = sum_k A(m,k) * B(n,k)
+//   A(m,k) = A[m*a_rs + k*a_cs],  B(n,k) = B[n*b_rs + k*b_cs]
+// 64x64x16 block tile, 4x4 register tile, 256 threads.
+// =========================================================================================
+constexpr int GB = 64, GK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_strided_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs,
+                     const float* __restrict__ B, int64_t b_rs, int64_t b_cs,
+                     float* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  __shared__ __align__(16) float As[GK][GB + 4];
+  __shared__ __align__(16) float Bs[GK][GB + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const bool a_kfast = (a_cs == 1), b_kfast = (b_cs == 1);
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + 256 * i;
+      int mm = a_kfast ? e / GK : e % GB, kk = a_kfast ? e % GK : e / GB;
+      int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[gm * a_rs + gk * a_cs] : 0.f;
+      int nn = b_kfast ? e / GK : e % GB;
+      kk = b_kfast ? e % GK : e / GB;
+      int gn = n0 + nn;
+      gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? B[gn * b_rs + gk * b_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn < N) C[gm * ldc + gn] = acc[i][j];
+    }
+  }
+}
+
+static int launch_sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
+                        float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  dim3 grid((N + GB - 1) / GB, (M + GB - 1) / GB);
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+// =========================================================================================
+// Region Gram  G_i = V_i V_i^T  (n_regions x n_regions per image), fp32.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+region_gram_kernel(const float* __restrict__ images, int R, int d, float* __restrict__ gram) {
+  extern __shared__ float sm[];   // [R][KC+1]
+  constexpr int KC = 128;
+  const float* V = images + (int64_t)blockIdx.x * R * d;
+  const int n_out = R * R;
+  float acc[8] = {};               // supports R*R <= 2048
+  for (int k0 = 0; k0 < d; k0 += KC) {
+    for (int e = threadIdx.x; e < R * KC; e += blockDim.x) {
+      int r = e / KC, k = e % KC;
+      sm[r * (KC + 1) + k] = (k0 + k < d) ? V[(int64_t)r * d + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      int idx = threadIdx.x + o * 256;
+      if (idx < n_out) {
+        const float* a = sm + (idx / R) * (KC + 1);
+        const float* b = sm + (idx % R) * (KC + 1);
+        float s = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < KC; ++k) s = fmaf(a[k], b[k], s);
+        acc[o] += s;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    int idx = threadIdx.x + o * 256;
+    if (idx < n_out) gram[(int64_t)blockIdx.x * n_out + idx] = acc[o];
+  }
+}
+
+// =========================================================================================
+// SCAN scores, fp32, all modes.  One block = one caption x 4 images.
+//   phase 1: raw affinities A[region][word] for the 4 images (register-tiled FMA), word and
+//            region norms, and (i2t) the caption's word Gram.
+//   phase 2: the reference's epilogue, written once for both directions in terms of
+//            source index s / query index q (func_attention, Objectives.py:421-476):
+//              t2i: s = region, q = word      i2t: s = word, q = region
+//            X[s][q]  -> raw_feature_norm over q -> softmax over s (x lambda_softmax)
+//            r[q] = cos(query_q, sum_s alpha[q][s] context_s)
+//                 = (sum_s alpha A[s][q]) / max(|query_q| * sqrt(alpha^T Gctx alpha), 1e-8)
+//            with Gctx the context Gram (regions: precomputed; words: built in phase 1).
+//   phase 3: aggregate r over q (LSE / Mean / Max / Sum).
+// =========================================================================================
+constexpr int SF_IMGS = 4;
+constexpr int SF_BK = 32;
+constexpr int SF_LMAX = ITR_MAX_WORDS_F32;   // 80
+constexpr int SF_LP = SF_LMAX + 1;           // padded row length of the A arrays
+
+struct ScanF32Params {
+  const float* images; const float* gram; const float* captions; const int32_t* cap_lens;
+  int n_img, R, n_cap, lmax, d;
+  int cross_attn, feature_norm, agg;
+  float lambda_softmax, lambda_lse;
+  float* scores; int64_t ld_scores;
+};
+
+template <int CPT>
+__device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, int n_rows, const float* W, int n,
+                                              float* Vs, float* Ws, float* Araw, float* qn_w, float* vn2, float* Gcap) {
+  // Vs[SF_BK][148], Ws[SF_BK][84]; thread (ty, tx): rows ty*9..ty*9+8, cols tx + 16*c
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int RT = SF_IMGS * p.R;    // 144 rows when R = 36
+  const int rpt = (RT + 15) / 16;  // rows per thread (9)
+  float acc[9][CPT];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[i][c] = 0.f;
+  float wn_acc = 0.f, vn_acc = 0.f;
+  for (int k0 = 0; k0 < p.d; k0 += SF_BK) {
+    for (int e = tid; e < RT * SF_BK; e += 256) {
+      int r = e / SF_BK, k = e % SF_BK;
+      float v = 0.f;
+      if (r < n_rows && k0 + k < p.d) v = p.images[((int64_t)img0 * p.R + r) * p.d + k0 + k];
+      Vs[k * 148 + r] = v;
+    }
+    for (int e = tid; e < SF_LMAX * SF_BK; e += 256) {
+      int j = e / SF_BK, k = e % SF_BK;
+      float v = 0.f;
+      if (j < n && k0 + k < p.d) v = W[(int64_t)j * p.d + k0 + k];
+      Ws[k * 84 + j] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < SF_BK; ++k) {
+      float wv[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) wv[c] = Ws[k * 84 + tx + 16 * c];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float vv = (i < rpt) ? Vs[k * 148 + ty * rpt + i] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(vv, wv[c], acc[i][c]);
+      }
+    }
+    // squared norms of words / regions, and the caption's word Gram (i2t only)
+    if (tid < n) {
+      float s = 0.f;
+      for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * 84 + tid], Ws[k * 84 + tid], s);
+      wn_acc += s;
+    }
+    if (tid < RT) {
+      float s = 0.f;
+      for (int k = 0; k < SF_BK; ++k) s = fmaf(Vs[k * 148 + tid], Vs[k * 148 + tid], s);
+      vn_acc += s;
+    }
+    if (p.cross_attn == ITR_I2T) {
+      for (int o = tid; o < n * n; o += 256) {
+        int a = o / n, b = o % n;
+        float s = 0.f;
+        for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * 84 + a], Ws[k * 84 + b], s);
+        Gcap[a * SF_LP + b] += s;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    int r = ty * rpt + i;
+    if (i < rpt && r < RT) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        int j = tx + 16 * c;
+        if (j < SF_LMAX) Araw[r * SF_LP + j] = acc[i][c];
+      }
+    }
+  }
+  if (tid < n) qn_w[tid] = sqrtf(wn_acc);
+  if (tid < RT) vn2[tid] = sqrtf(vn_acc);
+}
+
+__device__ __forceinline__ float leaky01(float x) { return x > 0.f ? x : 0.1f * x; }
+
+__global__ void __launch_bounds__(256)
+scan_f32_kernel(ScanF32Params p) {
+  extern __shared__ __align__(16) float smem[];
+  const int R = p.R, RT = SF_IMGS * R;
+  float* Vs = smem;                           // SF_BK*148
+  float* Ws = Vs + SF_BK * 148;               // SF_BK*84
+  float* Araw = Ws + SF_BK * 84;              // RT*SF_LP   raw affinities [row = img*R + region][word]
+  float* X = Araw + RT * SF_LP;               // RT*SF_LP   normalised / exponentiated copy
+  float* Gctx = X + RT * SF_LP;               // t2i: SF_IMGS*R*R region Grams; i2t: SF_LP*SF_LP word Gram
+  const int g_floats = max(SF_IMGS * R * R, SF_LP * SF_LP);
+  float* wnorm = Gctx + g_floats;             // SF_LMAX  |w_j|
+  float* vnorm = wnorm + SF_LMAX;             // RT       |v_k|
+  float* rsim = vnorm + RT;                   // SF_IMGS * max(R, SF_LMAX)
+  const int RS = max(R, SF_LMAX);
+
+  const int c = blockIdx.x;
+  const int img0 = blockIdx.y * SF_IMGS;
+  const int n_im = min(SF_IMGS, p.n_img - img0);
+  const int n = p.cap_lens[c];
+  const float* W = p.captions + (int64_t)c * p.lmax * p.d;
+  const int tid = threadIdx.x;
+  const bool t2i = (p.cross_attn == ITR_T2I);
+
+  if (t2i) {
+    for (int e = tid; e < n_im * R * R; e += 256) Gctx[e] = p.gram[(int64_t)img0 * R * R + e];
+  } else {
+    for (int e = tid; e < SF_LP * SF_LP; e += 256) Gctx[e] = 0.f;
+  }
+  __syncthreads();
+
+  const int cpt = (n + 15) / 16;
+  switch (cpt) {
+    case 1: scan_f32_gemm<1>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 2: scan_f32_gemm<2>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 3: scan_f32_gemm<3>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 4: scan_f32_gemm<4>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    default: scan_f32_gemm<5>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+  }
+  __syncthreads();
+
+  // index helpers: element (image m, source s, query q) of the [row][word] arrays
+  const int S = t2i ? R : n, Q = t2i ? n : R;
+  auto at = [&](float* base, int m, int s, int q) -> float& {
+    return t2i ? base[(m * R + s) * SF_LP + q] : base[(m * R + q) * SF_LP + s];
+  };
+
+  // ---- step 1: raw_feature_norm over q, for every (image, s) ---------------------------
+  for (int it = tid; it < n_im * S; it += 256) {
+    int m = it / S, s = it % S;
+    const int mode = p.feature_norm;
+    if (mode == ITR_NORM_CLIPPED_L2 || mode == ITR_NORM_L2) {
+      float ss = 0.f;
+      for (int q = 0; q < Q; ++q) {
+        float a = at(Araw, m, s, q);
+        if (mode == ITR_NORM_CLIPPED_L2) a = leaky01(a);
+        ss = fmaf(a, a, ss);
+      }
+      float inv = 1.f / (sqrtf(ss) + 1e-8f);
+      for (int q = 0; q < Q; ++q) {
+        float a = at(Araw, m, s, q);
+        if (mode == ITR_NORM_CLIPPED_L2) a = leaky01(a);
+        at(X, m, s, q) = a * inv;
+      }
+    } else if (mode == ITR_NORM_SOFTMAX) {
+      float mx = -FLT_MAX;
+      for (int q = 0; q < Q; ++q) mx = fmaxf(mx, at(Araw, m, s, q));
+      float z = 0.f;
+      for (int q = 0; q < Q; ++q) z += expf(at(Araw, m, s, q) - mx);
+      float inv = 1.f / z;
+      for (int q = 0; q < Q; ++q) at(X, m, s, q) = expf(at(Araw, m, s, q) - mx) * inv;
+    } else {
+      for (int q = 0; q < Q; ++q) {
+        float a = at(Araw, m, s, q);
+        at(X, m, s, q) = (mode == ITR_NORM_CLIPPED) ? leaky01(a) : a;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- step 2+3: softmax over s, attended cosine, for every (image, q) -------------------
+  for (int it = tid; it < n_im * Q; it += 256) {
+    int m = it / Q, q = it % Q;
+    float mx = -FLT_MAX;
+    for (int s = 0; s < S; ++s) mx = fmaxf(mx, at(X, m, s, q) * p.lambda_softmax);
+    float Z = 0.f, P = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float e = expf(at(X, m, s, q) * p.lambda_softmax - mx);
+      at(X, m, s, q) = e;
+      Z += e;
+      P = fmaf(e, at(Araw, m, s, q), P);
+    }
+    const float* G = t2i ? Gctx + m * R * R : Gctx;
+    const int gs = t2i ? R : SF_LP;
+    float Qf = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float u = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) u = fmaf(G[s * gs + s2], at(X, m, s2, q), u);
+      Qf = fmaf(at(X, m, s, q), u, Qf);
+    }
+    float qn = t2i ? wnorm[q] : vnorm[m * R + q];
+    float invZ = 1.f / Z;
+    float w12 = P * invZ;
+    float w2 = sqrtf(fmaxf(Qf, 0.f)) * invZ;
+    rsim[m * RS + q] = w12 / fmaxf(qn * w2, 1e-8f);
+  }
+  __syncthreads();
+
+  // ---- step 4: aggregate over q, one warp per image --------------------------------------
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < n_im) {
+    const float* r = rsim + warp * RS;
+    float v;
+    if (p.agg == ITR_AGG_MAX) {
+      v = -FLT_MAX;
+      for (int q = lane; q < Q; q += 32) v = fmaxf(v, r[q]);
+      v = warp_max(v);
+    } else {
+      v = 0.f;
+      for (int q = lane; q < Q; q += 32) v += (p.agg == ITR_AGG_LSE) ? expf(r[q] * p.lambda_lse) : r[q];
+      v = warp_sum(v);
+      if (p.agg == ITR_AGG_LSE) v = logf(v) / p.lambda_lse;
+      if (p.agg == ITR_AGG_MEAN) v = v / (float)Q;
+    }
+    if (lane == 0) p.scores[(int64_t)(img0 + warp) * p.ld_scores + c] = v;
+  }
+}
+
+// =========================================================================================
+// Hinge loss (fwd + bwd).  stats[i] = {row value, row arg / count, col value, col arg / count}
+// =========================================================================================
+__global__ void __launch_bounds__(128)
+hinge_stats_kernel(const float* __restrict__ S, int64_t ld, int n, float margin, int max_violation,
+                   float4* __restrict__ stats) {
+  __shared__ float sv[2][4];
+  __shared__ int si[2][4];
+  const int i = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float d = S[(int64_t)i * ld + i];
+  // row i: cost_s[i][j] = relu(margin + S[i][j] - d_i); column i: cost_im[j][i] = relu(margin + S[j][i] - d_i)
+  float rv = max_violation ? -1.f : 0.f, cv = rv;
+  int ra = 0x7fffffff, ca = 0x7fffffff, rc = 0, cc = 0;
+  for (int j = tid; j < n; j += 128) {
+    if (j == i) continue;
+    float a = fmaxf(margin + S[(int64_t)i * ld + j] - d, 0.f);
+    float b = fmaxf(margin + S[(int64_t)j * ld + i] - d, 0.f);
+    if (max_violation) {
+      if (a > rv) { rv = a; ra = j; }
+      if (b > cv) { cv = b; ca = j; }
+    } else {
+      rv += a; cv += b; rc += (a > 0.f); cc += (b > 0.f);
+    }
+  }
+  // block reduce: (max, lowest index) or (sum, count)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float orv = __shfl_xor_sync(0xffffffffu, rv, o), ocv = __shfl_xor_sync(0xffffffffu, cv, o);
+    int ora = __shfl_xor_sync(0xffffffffu, ra, o), oca = __shfl_xor_sync(0xffffffffu, ca, o);
+    int orc = __shfl_xor_sync(0xffffffffu, rc, o), occ = __shfl_xor_sync(0xffffffffu, cc, o);
+    if (max_violation) {
+      if (orv > rv || (orv == rv && ora < ra)) { rv = orv; ra = ora; }
+      if (ocv > cv || (ocv == cv && oca < ca)) { cv = ocv; ca = oca; }
+    } else {
+      rv += orv; cv += ocv; rc += orc; cc += occ;
+    }
+  }
+  if (lane == 0) { sv[0][warp] = rv; sv[1][warp] = cv; si[0][warp] = max_violation ? ra : rc; si[1][warp] = max_violation ? ca : cc; }
+  __syncthreads();
+  if (tid == 0) {
+    float R = sv[0][0], Cc = sv[1][0];
+    int RI = si[0][0], CI = si[1][0];
+    for (int w = 1; w < 4; ++w) {
+      if (max_violation) {
+        if (sv[0][w] > R || (sv[0][w] == R && si[0][w] < RI)) { R = sv[0][w]; RI = si[0][w]; }
+        if (sv[1][w] > Cc || (sv[1][w] == Cc && si[1][w] < CI)) { Cc = sv[1][w]; CI = si[1][w]; }
+      } else {
+        R += sv[0][w]; Cc += sv[1][w]; RI += si[0][w]; CI += si[1][w];
+      }
+    }
+    if (max_violation) { R = fmaxf(R, 0.f); Cc = fmaxf(Cc, 0.f); }   // n == 1: no negatives
+    stats[i] = make_float4(R, __int_as_float(RI), Cc, __int_as_float(CI));
+  }
+}
+
+// grid-stride over the n x n matrix; block 0 additionally reduces the loss in a fixed order.
+__global__ void __launch_bounds__(256)
+hinge_finish_kernel(const float* __restrict__ S, int64_t ld, int n, float margin, int max_violation,
+                    const float4* __restrict__ stats, float* __restrict__ loss,
+                    float* __restrict__ dS, int64_t ldd) {
+  if (blockIdx.x == 0) {
+    __shared__ float part[8];
+    float v = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) v += stats[i].x + stats[i].z;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += part[w];
+      *loss = t;
+    }
+  }
+  if (dS == nullptr) return;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < (int64_t)n * n; e += (int64_t)gridDim.x * 256) {
+    int i = (int)(e / n), j = (int)(e % n);
+    float g;
+    float4 si = stats[i];
+    if (i == j) {
+      g = max_violation ? -((si.x > 0.f) + (si.z > 0.f)) : -(float)(__float_as_int(si.y) + __float_as_int(si.w));
+    } else {
+      float4 sj = stats[j];
+      if (max_violation) {
+        g = (float)((__float_as_int(si.y) == j && si.x > 0.f) + (__float_as_int(sj.w) == i && sj.z > 0.f));
+      } else {
+        float s = S[(int64_t)i * ld + j];
+        float di = S[(int64_t)i * ld + i], dj = S[(int64_t)j * ld + j];
+        g = (float)((margin + s - di > 0.f) + (margin + s - dj > 0.f));
+      }
+    }
+    dS[(int64_t)i * ldd + j] = g;
+  }
+}
+
+// =========================================================================================
+// Ranking
+// =========================================================================================
+__global__ void rank_thresholds_kernel(const float* __restrict__ S, int64_t ld, int n_img, int n_cap, int cap_offset,
+                                       int cpi, float* __restrict__ thr_row, float* __restrict__ thr_col) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_cap) {
+    int g = (cap_offset + t) / cpi;
+    thr_col[t] = (g < n_img) ? S[(int64_t)g * ld + t] : INFINITY;
+  }
+  if (t < n_img) {
+    float best = -INFINITY;
+    for (int k = 0; k < cpi; ++k) {
+      int c = t * cpi + k - cap_offset;
+      if (c >= 0 && c < n_cap) best = fmaxf(best, S[(int64_t)t * ld + c]);
+    }
+    thr_row[t] = best;
+  }
+}
+
+// One block scans a [RK_ROWS x 256] tile: column stats stay in registers, row stats go
+// through a warp reduction; both are merged with atomics (integers / packed keys only, so
+// the result does not depend on the order of arrival).
+constexpr int RK_ROWS = 64;
+__global__ void __launch_bounds__(256)
+rank_count_kernel(const float* __restrict__ S, int64_t ld, int n_img, int n_cap, int cap_offset,
+                  const float* __restrict__ thr_row, const float* __restrict__ thr_col,
+                  int* __restrict__ cnt_row, int* __restrict__ cnt_col,
+                  unsigned long long* __restrict__ best_row, unsigned long long* __restrict__ best_col) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * RK_ROWS;
+  const int r1 = min(r0 + RK_ROWS, n_img);
+  const bool live = c < n_cap;
+  const float tc = live ? thr_col[c] : INFINITY;
+  const int lane = threadIdx.x & 31;
+  int ccnt = 0;
+  unsigned long long cbest = 0ull;
+  for (int r = r0; r < r1; ++r) {
+    float v = live ? S[(int64_t)r * ld + c] : -INFINITY;
+    ccnt += (v > tc);
+    unsigned long long key = live ? (((unsigned long long)orderable(v)) << 32) : 0ull;
+    unsigned long long ck = key | (unsigned)(~(unsigned)r);
+    cbest = ck > cbest ? ck : cbest;
+    // row side
+    int rc = warp_sum_i(live && v > thr_row[r]);
+    unsigned long long rk = live ? (key | (unsigned)(~(unsigned)(cap_offset + c))) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(0xffffffffu, rk, o);
+      rk = other > rk ? other : rk;
+    }
+    if (lane == 0) {
+      if (rc) atomicAdd(&cnt_row[r], rc);
+      atomicMax(&best_row[r], rk);
+    }
+  }
+  if (live) {
+    if (ccnt) atomicAdd(&cnt_col[c], ccnt);
+    atomicMax(&best_col[c], cbest);
+  }
+}
+
+
+// float64 variant for host matrices handed to i2t()/t2i() (evaluation.py ranks a float64
+// matrix, e.g. the average of two models' scores, which float32 cannot represent exactly).
+// Single block of the matrix, three passes: thresholds, counts + best value, arg of best.
+__device__ __forceinline__ unsigned long long orderable64(double f) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(f);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__global__ void rank64_thresholds_kernel(const double* __restrict__ S, int64_t ld, int n_img, int n_cap, int cpi,
+                                         double* __restrict__ thr_row, double* __restrict__ thr_col) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_cap) {
+    int g = t / cpi;
+    thr_col[t] = (g < n_img) ? S[(int64_t)g * ld + t] : INFINITY;
+  }
+  if (t < n_img) {
+    double best = -INFINITY;
+    for (int k = 0; k < cpi; ++k) {
+      int c = t * cpi + k;
+      if (c < n_cap) best = fmax(best, S[(int64_t)t * ld + c]);
+    }
+    thr_row[t] = best;
+  }
+}
+template <bool ARG>
+__global__ void __launch_bounds__(256)
+rank64_pass_kernel(const double* __restrict__ S, int64_t ld, int n_img, int n_cap,
+                   const double* __restrict__ thr_row, const double* __restrict__ thr_col,
+                   int* __restrict__ cnt_row, int* __restrict__ cnt_col,
+                   unsigned long long* __restrict__ best_row, unsigned long long* __restrict__ best_col,
+                   int* __restrict__ arg_row, int* __restrict__ arg_col) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * RK_ROWS, r1 = min(r0 + RK_ROWS, n_img);
+  if (c >= n_cap) return;
+  if (!ARG) {
+    const double tc = thr_col[c];
+    int ccnt = 0;
+    unsigned long long cb = 0ull;
+    for (int r = r0; r < r1; ++r) {
+      double v = S[(int64_t)r * ld + c];
+      ccnt += (v > tc);
+      unsigned long long key = orderable64(v);
+      cb = key > cb ? key : cb;
+      if (v > thr_row[r]) atomicAdd(&cnt_row[r], 1);
+      if (key > best_row[r]) atomicMax(&best_row[r], key);
+    }
+    if (ccnt) atomicAdd(&cnt_col[c], ccnt);
+    atomicMax(&best_col[c], cb);
+  } else {
+    const unsigned long long bc = best_col[c];
+    int ca = 0x7fffffff;
+    for (int r = r0; r < r1; ++r) {
+      unsigned long long key = orderable64(S[(int64_t)r * ld + c]);
+      if (key == bc && r < ca) ca = r;
+      if (key == best_row[r]) atomicMin(&arg_row[r], c);
+    }
+    if (ca != 0x7fffffff) atomicMin(&arg_col[c], ca);
+  }
+}
+
+}  // namespace itr
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace itr;
+
+extern "C" const char* itr_last_error(void) { return last_error().c_str(); }
+extern "C" int itr_version(void) { return 100; }
+
+extern "C" int itr_device_supported(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { fail(ITR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return -ITR_ERR_CUDA; }
+  return prop.major == 10 ? 1 : 0;
+}
+
+extern "C" int itr_cosine_scores_f32(const float* im, const float* s, int n_img, int n_cap, int d,
+                                     float* scores, int64_t ld_scores, void* stream) {
+  ITR_REQUIRE(im && s && scores, "itr_cosine_scores_f32: null pointer");
+  ITR_REQUIRE(n_img >= 0 && n_cap >= 0 && d > 0 && ld_scores >= n_cap, "itr_cosine_scores_f32: bad shape");
+  if (n_img == 0 || n_cap == 0) return ITR_OK;
+  return launch_sgemm(im, d, 1, s, d, 1, scores, ld_scores, n_img, n_cap, d, as_stream(stream));
+}
+
+extern "C" int itr_region_gram_f32(const float* images, int n_img, int n_regions, int d, float* gram, void* stream) {
+  ITR_REQUIRE(images && gram, "itr_region_gram_f32: null pointer");
+  ITR_REQUIRE(n_regions > 0 && n_regions * n_regions <= 2048 && d > 0, "itr_region_gram_f32: n_regions must be in [1, 45]");
+  if (n_img <= 0) return ITR_OK;
+  size_t smem = (size_t)n_regions * 129 * sizeof(float);
+  region_gram_kernel<<<n_img, 256, smem, as_stream(stream)>>>(images, n_regions, d, gram);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_scan_scores_f32(const float* images, const float* gram, const float* captions,
+                                   const int32_t* cap_lens, int n_img, int n_regions, int n_cap, int lmax, int d,
+                                   int cross_attn, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
+                                   float* scores, int64_t ld_scores, void* stream) {
+  ITR_REQUIRE(images && captions && cap_lens && scores, "itr_scan_scores_f32: null pointer");
+  ITR_REQUIRE(cross_attn == ITR_T2I || cross_attn == ITR_I2T, "unknown cross_attn: %d", cross_attn);
+  ITR_REQUIRE(feature_norm >= 0 && feature_norm <= ITR_NORM_NONE, "unknown first norm type: %d", feature_norm);
+  ITR_REQUIRE(agg >= 0 && agg <= ITR_AGG_SUM, "unknown aggfunc: %d", agg);
+  ITR_REQUIRE(n_regions == ITR_REGIONS, "itr_scan_scores_f32: built for %d regions per image, got %d", ITR_REGIONS, n_regions);
+  ITR_REQUIRE(lmax >= 1 && lmax <= ITR_MAX_WORDS_F32, "itr_scan_scores_f32: padded caption width %d outside [1, %d]", lmax, ITR_MAX_WORDS_F32);
+  ITR_REQUIRE(cross_attn == ITR_I2T || gram != nullptr, "itr_scan_scores_f32: t2i needs the region Gram");
+  ITR_REQUIRE(d > 0 && ld_scores >= n_cap, "itr_scan_scores_f32: bad shape");
+  if (n_img <= 0 || n_cap <= 0) return ITR_OK;
+  ScanF32Params p{images, gram, captions, cap_lens, n_img, n_regions, n_cap, lmax, d,
+                  cross_attn, feature_norm, agg, lambda_softmax, lambda_lse, scores, ld_scores};
+  const int RT = SF_IMGS * n_regions;
+  int g_floats = SF_IMGS * n_regions * n_regions;
+  if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
+  int rs = n_regions > SF_LMAX ? n_regions : SF_LMAX;
+  size_t smem = sizeof(float) * ((size_t)SF_BK * 148 + SF_BK * 84 + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
+  ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_cap, (n_img + SF_IMGS - 1) / SF_IMGS);
+  ITR_REQUIRE(grid.y <= 65535, "itr_scan_scores_f32: more than %d images per call", 65535 * SF_IMGS);
+  scan_f32_kernel<<<grid, 256, smem, as_stream(stream)>>>(p);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_hinge_fwd_bwd_f32(const float* scores, int64_t ld_scores, int n, float margin, int max_violation,
+                                     float* loss, float* dscores, int64_t ld_dscores, void* stream) {
+  ITR_REQUIRE(scores && loss, "itr_hinge_fwd_bwd_f32: null pointer");
+  ITR_REQUIRE(n >= 1 && ld_scores >= n && (dscores == nullptr || ld_dscores >= n), "itr_hinge_fwd_bwd_f32: bad shape");
+  cudaStream_t st = as_stream(stream);
+  float4* stats = nullptr;
+  ITR_CHECK_CUDA(cudaMallocAsync(&stats, sizeof(float4) * n, st));
+  hinge_stats_kernel<<<n, 128, 0, st>>>(scores, ld_scores, n, margin, max_violation, stats);
+  int blocks = dscores ? (int)(((int64_t)n * n + 255) / 256) : 1;
+  if (blocks > 1184) blocks = 1184;
+  hinge_finish_kernel<<<blocks, 256, 0, st>>>(scores, ld_scores, n, margin, max_violation, stats, loss, dscores, ld_dscores);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(stats, st);
+  ITR_CHECK_CUDA(e);
+  return ITR_OK;
+}
+
+extern "C" int itr_cosine_hinge_fwd_bwd_f32(const float* im, const float* s, int n, int d, float margin,
+                                            int max_violation, float* ws, float* loss, float* d_im, float* d_s,
+                                            void* stream) {
+  ITR_REQUIRE(im && s && ws && loss, "itr_cosine_hinge_fwd_bwd_f32: null pointer");
+  ITR_REQUIRE(n >= 1 && d >= 1, "itr_cosine_hinge_fwd_bwd_f32: bad shape");
+  cudaStream_t st = as_stream(stream);
+  float* S = ws;
+  float* dS = ws + (int64_t)n * n;
+  const bool need_grad = d_im != nullptr || d_s != nullptr;
+  int rc = launch_sgemm(im, d, 1, s, d, 1, S, n, n, n, d, st);
+  if (rc) return rc;
+  rc = itr_hinge_fwd_bwd_f32(S, n, n, margin, max_violation, loss, need_grad ? dS : nullptr, n, stream);
+  if (rc) return rc;
+  // d_im[i][k] = sum_j dS[i][j] s[j][k]   ;   d_s[j][k] = sum_i dS[i][j] im[i][k]
+  if (d_im) { rc = launch_sgemm(dS, n, 1, s, 1, d, d_im, d, n, d, n, st); if (rc) return rc; }
+  if (d_s) { rc = launch_sgemm(dS, 1, n, im, 1, d, d_s, d, n, d, n, st); if (rc) return rc; }
+  return ITR_OK;
+}
+
+extern "C" int itr_rank_thresholds_f32(const float* scores, int64_t ld_scores, int n_img, int n_cap_local,
+                                       int cap_offset, int caps_per_img, float* thr_row, float* thr_col, void* stream) {
+  ITR_REQUIRE(scores && thr_row && thr_col, "itr_rank_thresholds_f32: null pointer");
+  ITR_REQUIRE(n_img >= 1 && n_cap_local >= 1 && caps_per_img >= 1 && cap_offset >= 0 && ld_scores >= n_cap_local,
+              "itr_rank_thresholds_f32: bad shape");
+  int n = n_img > n_cap_local ? n_img : n_cap_local;
+  rank_thresholds_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(scores, ld_scores, n_img, n_cap_local, cap_offset,
+                                                                        caps_per_img, thr_row, thr_col);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_rank_count_f32(const float* scores, int64_t ld_scores, int n_img, int n_cap_local, int cap_offset,
+                                  const float* thr_row, const float* thr_col, int32_t* cnt_row, int32_t* cnt_col,
+                                  uint64_t* best_row, uint64_t* best_col, void* stream) {
+  ITR_REQUIRE(scores && thr_row && thr_col && cnt_row && cnt_col && best_row && best_col, "itr_rank_count_f32: null pointer");
+  ITR_REQUIRE(n_img >= 1 && n_cap_local >= 1 && ld_scores >= n_cap_local, "itr_rank_count_f32: bad shape");
+  cudaStream_t st = as_stream(stream);
+  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_row, 0, sizeof(int32_t) * n_img, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, sizeof(int32_t) * n_cap_local, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(best_row, 0, sizeof(uint64_t) * n_img, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, sizeof(uint64_t) * n_cap_local, st));
+  dim3 grid((n_cap_local + 255) / 256, (n_img + RK_ROWS - 1) / RK_ROWS);
+  rank_count_kernel<<<grid, 256, 0, st>>>(scores, ld_scores, n_img, n_cap_local, cap_offset, thr_row, thr_col, cnt_row,
+                                          cnt_col, reinterpret_cast<unsigned long long*>(best_row),
+                                          reinterpret_cast<unsigned long long*>(best_col));
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_rank_f64(const double* scores, int64_t ld_scores, int n_img, int n_cap, int caps_per_img,
+                            int32_t* rank_row, int32_t* rank_col, int32_t* top1_row, int32_t* top1_col, void* stream) {
+  ITR_REQUIRE(scores && rank_row && rank_col && top1_row && top1_col, "itr_rank_f64: null pointer");
+  ITR_REQUIRE(n_img >= 1 && n_cap >= 1 && caps_per_img >= 1 && ld_scores >= n_cap, "itr_rank_f64: bad shape");
+  cudaStream_t st = as_stream(stream);
+  double *thr_row = nullptr, *thr_col = nullptr;
+  unsigned long long *best_row = nullptr, *best_col = nullptr;
+  ITR_CHECK_CUDA(cudaMallocAsync(&thr_row, sizeof(double) * (n_img + n_cap), st));
+  thr_col = thr_row + n_img;
+  ITR_CHECK_CUDA(cudaMallocAsync(&best_row, sizeof(unsigned long long) * (n_img + n_cap), st));
+  best_col = best_row + n_img;
+  cudaMemsetAsync(best_row, 0, sizeof(unsigned long long) * (n_img + n_cap), st);
+  cudaMemsetAsync(rank_row, 0, sizeof(int32_t) * n_img, st);
+  cudaMemsetAsync(rank_col, 0, sizeof(int32_t) * n_cap, st);
+  cudaMemsetAsync(top1_row, 0x7f, sizeof(int32_t) * n_img, st);
+  cudaMemsetAsync(top1_col, 0x7f, sizeof(int32_t) * n_cap, st);
+  int n = n_img > n_cap ? n_img : n_cap;
+  rank64_thresholds_kernel<<<(n + 255) / 256, 256, 0, st>>>(scores, ld_scores, n_img, n_cap, caps_per_img, thr_row, thr_col);
+  dim3 grid((n_cap + 255) / 256, (n_img + RK_ROWS - 1) / RK_ROWS);
+  rank64_pass_kernel<false><<<grid, 256, 0, st>>>(scores, ld_scores, n_img, n_cap, thr_row, thr_col, rank_row, rank_col,
+                                                  best_row, best_col, top1_row, top1_col);
+  rank64_pass_kernel<true><<<grid, 256, 0, st>>>(scores, ld_scores, n_img, n_cap, thr_row, thr_col, rank_row, rank_col,
+                                                 best_row, best_col, top1_row, top1_col);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(thr_row, st);
+  cudaFreeAsync(best_row, st);
+  ITR_CHECK_CUDA(e);
+  return ITR_OK;
+}

@@ -1,0 +1,185 @@
+"""Drop-ins for the hot-path symbols of ``itr.metricmodule.evaluation``:
+``cal_sims`` (:124-153), ``i2t`` (:156-189), ``t2i`` (:192-222), ``cal_recall`` (:225-259),
+plus the fused ``cal_sims_and_recall`` that ranks on the device and never ships the
+matrix to the host unless asked.
+
+Differences from the reference, all deliberate:
+  D1  every caption is scored with ITS OWN length.  The reference hands the un-sliced
+      ``lengths`` array to every caption block, so caption c is scored with
+      ``lengths[c % shard_size]``; pass ``compat_unsliced_lengths=True`` to reproduce that.
+  --  ``shard_size`` is accepted and ignored by the fused similarity functions (the whole
+      matrix is produced in one launch); it still drives the blocked loop used for callables
+      this package does not accelerate (``model.sim_enc``, ``model.mvm``).
+  --  rank = number of scores strictly greater than the ground-truth score.  Identical to the
+      reference's argsort position unless another score ties exactly with the ground truth,
+      where numpy's unstable sort leaves the reference's own answer unspecified.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import objectives, ops
+
+CAPS_PER_IMG = 5   # hard-coded upstream, evaluation.py:173,208
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("itr_b200 needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(x, dev):
+    """host numpy / tensor -> CUDA f32 tensor (pinned tensors copy asynchronously)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.to(dev, non_blocking=True)
+
+
+def _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths):
+    if lengths is None:
+        return None
+    ln = ops.lengths_to_numpy(lengths, n_cap) if not compat_unsliced_lengths else np.asarray(lengths, dtype=np.int32)
+    if compat_unsliced_lengths:
+        ln = ln[np.arange(n_cap) % shard_size]     # what evaluation.py:149 + Objectives.py:340 amount to
+    return ln
+
+
+def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False):
+    """The score matrix as a CUDA float32 tensor (n_img, n_cap); inputs host or device."""
+    dev = _device()
+    config = model.config
+    if config["name"] in ["CAMERA"]:
+        cal_fun = model.mvm
+    else:
+        cal_fun = model.sim_enc if getattr(model, "sim_enc", None) is not None else model.criterion.sim
+    n_img, n_cap = len(img_embs), len(cap_embs)
+    ln = _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths)
+
+    fused = cal_fun in (objectives.cosine_sim, objectives.xattn_score_t2i, objectives.xattn_score_i2t)
+    with torch.no_grad():
+        if fused:
+            img = _to_device(img_embs, dev)
+            if cal_fun is objectives.cosine_sim:
+                return ops.cosine_scores(img, _to_device(cap_embs, dev))
+            norm, agg = config["raw_feature_norm"], config["agg_func"]
+            if (cal_fun is objectives.xattn_score_t2i and objectives._precision(config) == "bf16"
+                    and img.dim() == 3 and img.size(1) == 36 and img.size(2) == 1024 and norm in ("clipped_l2norm", "l2norm")
+                    and int(np.max(ln)) <= 128):
+                caps = cap_embs if isinstance(cap_embs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cap_embs))
+                if caps.dtype != torch.float32:
+                    caps = caps.float()
+                if not caps.is_cuda and not caps.is_pinned():
+                    caps = caps.to(dev)          # pageable host memory: one plain copy
+                pi = ops.prepare_images(img)
+                pc = ops.prepare_captions(caps, ln, device=dev)   # pinned host memory is gathered in place
+                return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, config["lambda_softmax"], config.get("lambda_lse", 6.0))
+            return cal_fun(img, _to_device(cap_embs, dev), ln, config)
+        # anything else (learned similarity heads, CAMERA): the reference's blocked loop, with sliced lengths
+        out = torch.empty(n_img, n_cap, device=dev, dtype=torch.float32)
+        for i0 in range(0, n_img, shard_size):
+            i1 = min(i0 + shard_size, n_img)
+            img_block = _to_device(img_embs[i0:i1], dev)
+            for c0 in range(0, n_cap, shard_size):
+                c1 = min(c0 + shard_size, n_cap)
+                cap_block = _to_device(cap_embs[c0:c1], dev)
+                out[i0:i1, c0:c1] = cal_fun(img_block, cap_block, None if ln is None else ln[c0:c1], config)
+        return out
+
+
+def cal_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False):
+    """evaluation.py:124-153: host numpy in, host float64 (n_img, n_cap) out."""
+    t0 = time.time()
+    d = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths)
+    out = d.cpu().numpy().astype(np.float64)
+    print("Calculate similarity matrix elapses: {:.3f}s".format(time.time() - t0))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- ranking
+def _metrics(ranks):
+    n = len(ranks)
+    r1 = 100.0 * len(np.where(ranks < 1)[0]) / n
+    r5 = 100.0 * len(np.where(ranks < 5)[0]) / n
+    r10 = 100.0 * len(np.where(ranks < 10)[0]) / n
+    medr = np.floor(np.median(ranks)) + 1
+    meanr = ranks.mean() + 1
+    return (r1, r5, r10, medr, meanr)
+
+
+def device_ranks(sims_dev, caps_per_img=CAPS_PER_IMG):
+    """(i2t_ranks, i2t_top1, t2i_ranks, t2i_top1) as int64 CUDA tensors from a CUDA matrix (f32 or f64)."""
+    if sims_dev.dtype == torch.float64:
+        rr, rc, tr, tc = ops.rank_f64(sims_dev.contiguous(), caps_per_img)
+        return rr.long(), tr.long(), rc.long(), tc.long()
+    s = sims_dev if (sims_dev.dtype == torch.float32 and sims_dev.stride(1) == 1) else sims_dev.float().contiguous()
+    thr_row, thr_col = ops.rank_thresholds(s, 0, caps_per_img)
+    cnt_row, cnt_col, best_row, best_col = ops.rank_count(s, thr_row, thr_col, 0)
+    return cnt_row.long(), ops.unpack_best_index(best_row), cnt_col.long(), ops.unpack_best_index(best_col)
+
+
+def _rank_host(sims):
+    dev = _device()
+    if isinstance(sims, torch.Tensor):
+        s = sims.to(dev)
+    else:
+        s = torch.from_numpy(np.ascontiguousarray(sims)).to(dev)
+    if s.dtype not in (torch.float32, torch.float64):
+        s = s.double()
+    return [x.cpu().numpy().astype(np.float64) for x in device_ranks(s)]
+
+
+def i2t(sims, return_ranks=False):
+    """evaluation.py:156-189.  sims (N, 5N) -> (r1, r5, r10, medr, meanr)[, (ranks, top1)]."""
+    ranks, top1, _, _ = _rank_host(sims)
+    m = _metrics(ranks)
+    return (m, (ranks, top1)) if return_ranks else m
+
+
+def t2i(sims, return_ranks=False):
+    """evaluation.py:192-222."""
+    _, _, ranks, top1 = _rank_host(sims)
+    m = _metrics(ranks)
+    return (m, (ranks, top1)) if return_ranks else m
+
+
+def _recall_dict(r, rt, ri, rti, verbose=True):
+    ar = (r[0] + r[1] + r[2]) / 3
+    ari = (ri[0] + ri[1] + ri[2]) / 3
+    rsum = r[0] + r[1] + r[2] + ri[0] + ri[1] + ri[2]
+    if verbose:
+        print("rsum: %.1f" % rsum)
+        print("Average i2t Recall: %.1f" % ar)
+        print("Image to text: r1 %.1f; r5 %.1f; r10 %.1f; medr %.1f; meanr %.1f" % r)
+        print("Average t2i Recall: %.1f" % ari)
+        print("Text to image: r1 %.1f; r5 %.1f; r10 %.1f; medr %.1f; meanr %.1f" % ri)
+    return {
+        "result": [list(r) + list(ri) + [ar, ari, rsum]], "rsum": rsum,
+        "i2t_ave_r": ar, "i2t_r1": r[0], "i2t_r5": r[1], "i2t_r10": r[2], "i2t_medr": r[3], "i2t_meanr": r[4],
+        "i2t_ranks": rt[0], "i2t_top1": rt[1],
+        "t2i_ave_r": ari, "t2i_r1": ri[0], "t2i_r5": ri[1], "t2i_r10": ri[2], "t2i_medr": ri[3], "t2i_meanr": ri[4],
+        "t2i_ranks": rti[0], "t2i_top1": rti[1],
+    }
+
+
+def cal_recall(sims, verbose=True):
+    """evaluation.py:225-259: same dict keys; one upload, both directions ranked in one pass."""
+    a, b, c, d = _rank_host(sims)
+    return _recall_dict(_metrics(a), (a, b), _metrics(c), (c, d), verbose)
+
+
+def cal_sims_and_recall(model, img_embs, cap_embs, lengths=None, shard_size=128, return_sims=False, verbose=False,
+                        compat_unsliced_lengths=False):
+    """Fused evaluation: scores and both rankings stay on the device; only the (N,) / (5N,) rank and
+    top-1 vectors come back (plus the matrix when ``return_sims``)."""
+    sims = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths)
+    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in device_ranks(sims)]
+    res = _recall_dict(_metrics(a), (a, b), _metrics(c), (c, d), verbose)
+    if return_sims:
+        res["sims"] = sims
+    return res

@@ -1,0 +1,210 @@
+"""Drop-ins for the hot-path symbols of ``itr.modalmodule.Objectives`` (same names,
+argument meaning and error behaviour; reference lines cited per symbol).
+
+Precision modes (config key ``itr_b200_precision`` or env ``ITR_B200_PRECISION``):
+  "bf16" (default where available)  tcgen05 tensor-core kernel: inputs rounded to bf16,
+          fp32 accumulate -- SCAN t2i with raw_feature_norm in {clipped_l2norm, l2norm},
+          36 regions, embed 1024.  Scores within 1e-3 relative of the reference fed the
+          same rounded inputs.
+  "fp32"  CUDA-core float32 kernels: every mode / direction, within 1e-5 relative.
+Anything the bf16 kernel does not cover runs in fp32 mode -- on the GPU, never on the CPU.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+def _precision(config):
+    mode = None
+    if isinstance(config, dict):
+        mode = config.get("itr_b200_precision")
+    mode = mode or os.environ.get("ITR_B200_PRECISION") or "bf16"
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("itr_b200_precision must be 'bf16' or 'fp32', got {!r}".format(mode))
+    return mode
+
+
+def _no_grad_inputs(*tensors):
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "itr_b200: the fused SCAN scorer has no backward yet (SURVEY.md section 8(f), row f3); "
+            "call it under torch.no_grad() / on detached embeddings, or train SCAN with the reference scorer")
+
+
+# ---------------------------------------------------------------------------------------------
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """Objectives.py:10-15.  Compatibility helper (torch ops on the caller's device); the fused
+    scorers never materialise the D-wide operands this function needs."""
+    w12 = torch.sum(x1 * x2, dim)
+    w1 = torch.norm(x1, 2, dim)
+    w2 = torch.norm(x2, 2, dim)
+    return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
+
+
+def cosine_sim(im, s, *args):
+    """Objectives.py:18-21: all-pairs dot product of unit-norm embeddings, (n_img, n_cap)."""
+    if torch.is_grad_enabled() and (im.requires_grad or s.requires_grad):
+        return _CosineScores.apply(im, s)
+    return ops.cosine_scores(im, s)
+
+
+class _CosineScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, im, s):
+        ctx.save_for_backward(im, s)
+        return ops.cosine_scores(im, s)
+
+    @staticmethod
+    def backward(ctx, g):
+        im, s = ctx.saved_tensors
+        g = g.contiguous()
+        # d_im = g @ s, d_s = g.T @ im -- two more calls of the same kernel on transposed views
+        d_im = ops.cosine_scores(g, s.t().contiguous()) if ctx.needs_input_grad[0] else None
+        d_s = ops.cosine_scores(g.t().contiguous(), im.t().contiguous()) if ctx.needs_input_grad[1] else None
+        return d_im, d_s
+
+
+def order_sim(im, s, *args):
+    """Objectives.py:24-30 (out of the accelerated scope; kept so measure='order' still works)."""
+    ymx = s.unsqueeze(1).expand(s.size(0), im.size(0), s.size(1)) - im.unsqueeze(0).expand(s.size(0), im.size(0), s.size(1))
+    return -ymx.clamp(min=0).pow(2).sum(2).sqrt().t()
+
+
+def _scan(images, captions, cap_lens, config, cross_attn):
+    _no_grad_inputs(images, captions)
+    norm, agg = config["raw_feature_norm"], config["agg_func"]
+    lam_sm = config["lambda_softmax"]
+    lam_lse = config.get("lambda_lse", 6.0) if isinstance(config, dict) else config["lambda_lse"]
+    if agg not in ("LogSumExp", "Mean", "Max", "Sum"):
+        raise ValueError("unknown aggfunc: {}".format(agg))
+    if norm in ("l1norm", "clipped_l1norm"):
+        # the reference raises NameError here (undefined l1norm_d, defect D4)
+        raise ValueError("raw_feature_norm {!r} is not implemented by the reference either".format(norm))
+    images, captions = images.detach(), captions.detach()
+    if cross_attn == "t2i" and _precision(config) == "bf16" and ops.tc_supported(images, captions, norm):
+        ln = ops.lengths_to_numpy(cap_lens, captions.size(0))
+        if ln.max(initial=0) <= 128:
+            pi = ops.prepare_images(images)
+            pc = ops.prepare_captions(captions, ln)
+            return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, lam_sm, lam_lse)
+    return ops.scan_scores_f32(images, captions, cap_lens, cross_attn, norm, agg, lam_sm, lam_lse)
+
+
+def xattn_score_t2i(images, captions, cap_lens, config):
+    """Objectives.py:329-372.  images (n_image, n_regions, d), captions (n_caption, max_n_word, d),
+    cap_lens (n_caption) -> (n_image, n_caption).  Caption c uses words [0, cap_lens[c])."""
+    return _scan(images, captions, cap_lens, config, "t2i")
+
+
+def xattn_score_i2t(images, captions, cap_lens, config):
+    """Objectives.py:376-417."""
+    return _scan(images, captions, cap_lens, config, "i2t")
+
+
+def func_attention(query, context, config, smooth, eps=1e-8):
+    """Objectives.py:421-476.  Compatibility helper returning (weightedContext, attnT) with torch
+    ops on the caller's device.  The fused scorers above do NOT call it: they never build the
+    (batch, queryL, d) context tensor."""
+    attn = torch.bmm(context, query.transpose(1, 2))
+    mode = config["raw_feature_norm"]
+    if mode == "softmax":
+        attn = torch.softmax(attn, dim=2)
+    elif mode == "l2norm":
+        attn = attn / (attn.pow(2).sum(dim=2, keepdim=True).sqrt() + eps)
+    elif mode == "clipped_l2norm":
+        attn = nn.functional.leaky_relu(attn, 0.1)
+        attn = attn / (attn.pow(2).sum(dim=2, keepdim=True).sqrt() + eps)
+    elif mode == "clipped":
+        attn = nn.functional.leaky_relu(attn, 0.1)
+    elif mode != "no_norm":
+        raise ValueError("unknown first norm type:", mode)
+    attn = torch.softmax(attn.transpose(1, 2) * smooth, dim=2)
+    attn_t = attn.transpose(1, 2).contiguous()
+    weighted = torch.bmm(context.transpose(1, 2), attn_t).transpose(1, 2)
+    return weighted, attn_t
+
+
+# ---------------------------------------------------------------------------------------------
+class _Hinge(torch.autograd.Function):
+    """loss(scores) with the analytic gradient produced by the same kernel launch."""
+
+    @staticmethod
+    def forward(ctx, scores, margin, max_violation):
+        loss, ds = ops.hinge(scores, margin, max_violation, need_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(ds)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        return ds * g, None, None
+
+
+class _CosineHinge(torch.autograd.Function):
+    """VSE++ step: scores GEMM + hinge + both embedding gradients in one native call."""
+
+    @staticmethod
+    def forward(ctx, im, s, margin, max_violation):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        loss, d_im, d_s = ops.cosine_hinge(im, s, margin, max_violation, need_grad=need)
+        ctx.save_for_backward(d_im, d_s)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_im, d_s = ctx.saved_tensors
+        return (d_im * g if ctx.needs_input_grad[0] else None, d_s * g if ctx.needs_input_grad[1] else None, None, None)
+
+
+class ContrastiveLoss(nn.Module):
+    """Objectives.py:34-115.  Same constructor, same ``.sim`` attribute (``cal_sims`` reads
+    ``model.criterion.sim``, evaluation.py:131), same dispatch and ValueErrors."""
+
+    def __init__(self, config, margin=0, measure=None, max_violation=False):
+        super().__init__()
+        self.config = config
+        self.margin = margin
+        self.max_violation = max_violation
+        if measure == "order":
+            self.sim = order_sim
+        elif measure == "cosine":
+            self.sim = cosine_sim
+        else:
+            raise ValueError("unknown measure:", measure)
+        name = self.config["name"]
+        if name == "SAEM":
+            # SAEM's pdist similarities are outside the accelerated path
+            from itr.modalmodule import Objectives as _ref   # the reference package this drop-in is installed into
+            self.sim = _ref.pdist if measure == "order" else _ref.pdist_cos
+        elif name == "SCAN":
+            if self.config["cross_attn"] == "t2i":
+                self.sim = xattn_score_t2i
+            elif self.config["cross_attn"] == "i2t":
+                self.sim = xattn_score_i2t
+            else:
+                raise ValueError("unknown first norm type:", self.config["raw_feature_norm"])
+        elif name == "SGRAF":
+            self.sim = lambda x, y, m, n: x
+
+    def forward(self, im, s=None, s_l=None):
+        if self.sim is cosine_sim:
+            return _CosineHinge.apply(im, s, self.margin, self.max_violation)
+        scores = self.sim(im, s, s_l, self.config)
+        return _Hinge.apply(scores, self.margin, self.max_violation)
+
+
+class TripletLoss(nn.Module):
+    """Objectives.py:482-517: the same hinge on a ready score matrix (CAMERA)."""
+
+    def __init__(self, margin=0, max_violation=False):
+        super().__init__()
+        self.margin = margin
+        self.max_violation = max_violation
+
+    def forward(self, scores):
+        return _Hinge.apply(scores, self.margin, self.max_violation)

@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (device memory, streams and nothing else).
+
+Every function takes CUDA tensors, launches on the current torch stream and returns CUDA
+tensors.  There is no CPU path: a CPU tensor is an error.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from ._capi import check, ptr, stream_ptr
+
+
+def _cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("{} must be a torch tensor".format(name))
+    if not t.is_cuda:
+        raise RuntimeError("{} lives on {}; itr_b200 runs on CUDA only (no CPU fallback)".format(name, t.device))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def lengths_to_numpy(cap_lens, n_cap):
+    """cap_lens may be a list, numpy array or tensor (the reference indexes it per caption)."""
+    if isinstance(cap_lens, torch.Tensor):
+        cap_lens = cap_lens.detach().cpu().numpy()
+    ln = np.ascontiguousarray(np.asarray(cap_lens)[:n_cap], dtype=np.int32)
+    if ln.shape[0] != n_cap:
+        raise ValueError("cap_lens has {} entries for {} captions".format(ln.shape[0], n_cap))
+    return ln
+
+
+# ------------------------------------------------------------------------------ VSE++
+def cosine_scores(im, s):
+    im, s = _cuda_f32(im, "im"), _cuda_f32(s, "s")
+    if im.dim() != 2 or s.dim() != 2 or im.size(1) != s.size(1):
+        raise ValueError("cosine_sim expects (n_img, d) and (n_cap, d) embeddings, got {} and {}".format(
+            tuple(im.shape), tuple(s.shape)))
+    out = torch.empty(im.size(0), s.size(0), device=im.device, dtype=torch.float32)
+    with torch.cuda.device(im.device):
+        check(capi.lib().itr_cosine_scores_f32(ptr(im), ptr(s), im.size(0), s.size(0), im.size(1), ptr(out),
+                                               out.stride(0) if out.numel() else s.size(0), stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------ SCAN, fp32 mode
+def scan_scores_f32(images, captions, cap_lens, cross_attn, raw_feature_norm, agg_func, lambda_softmax, lambda_lse):
+    images, captions = _cuda_f32(images, "images"), _cuda_f32(captions, "captions")
+    n_img, n_reg, d = images.shape
+    n_cap, lmax, d2 = captions.shape
+    if d != d2:
+        raise ValueError("embedding sizes differ: {} vs {}".format(d, d2))
+    ln = lengths_to_numpy(cap_lens, n_cap)
+    if n_cap and (ln.min() < 1 or ln.max() > lmax):
+        raise ValueError("caption lengths must be in [1, {}]".format(lmax))
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    if cross_attn not in ("t2i", "i2t"):
+        raise ValueError("unknown cross_attn: {}".format(cross_attn))
+    lens_dev = torch.from_numpy(ln).to(images.device)
+    out = torch.empty(n_img, n_cap, device=images.device, dtype=torch.float32)
+    L = capi.lib()
+    with torch.cuda.device(images.device):
+        gram = None
+        if cross_attn == "t2i":
+            gram = torch.empty(n_img, n_reg, n_reg, device=images.device, dtype=torch.float32)
+            check(L.itr_region_gram_f32(ptr(images), n_img, n_reg, d, ptr(gram), stream_ptr()))
+        check(L.itr_scan_scores_f32(ptr(images), ptr(gram), ptr(captions), ptr(lens_dev), n_img, n_reg, n_cap, lmax, d,
+                                    capi.T2I if cross_attn == "t2i" else capi.I2T, norm, agg,
+                                    float(lambda_softmax), float(lambda_lse), ptr(out), max(n_cap, 1), stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------ SCAN t2i, tensor cores
+@dataclass
+class PreparedImages:
+    images_bf16: torch.Tensor     # (n_img, 36, 1024) bf16
+    gram_tri: torch.Tensor        # (n_img, 720) f32
+    n_img: int
+
+
+@dataclass
+class PreparedCaptions:
+    words_bf16: torch.Tensor      # (n_tiles*128, 1024) bf16
+    row_meta: torch.Tensor        # (n_tiles*128, 4) i32, device
+    row_wnorm: torch.Tensor       # (n_tiles*128,) f32
+    n_tiles: int
+    n_cap: int
+    sum_len: int
+
+
+def tc_supported(images, captions, raw_feature_norm, cap_lens=None):
+    """Shapes / modes the tcgen05 kernel is built for."""
+    return (images.dim() == 3 and captions.dim() == 3 and images.size(1) == capi.REGIONS
+            and images.size(2) == capi.EMBED and captions.size(2) == capi.EMBED
+            and raw_feature_norm in ("clipped_l2norm", "l2norm"))
+
+
+def plan_words(lengths: np.ndarray):
+    """Host-side bin packing (csrc/plan.cpp).  Returns (row_meta i32 (n_tiles*128, 4), n_tiles)."""
+    lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+    L = capi.lib()
+    n_tiles = L.itr_scan_plan_max_tiles(lengths.ctypes.data, len(lengths))
+    if n_tiles < 0:
+        check(-n_tiles)
+    meta = np.empty((max(n_tiles, 1) * capi.TILE_WORDS, 4), dtype=np.int32)
+    got = capi.C.c_int(0)
+    check(L.itr_scan_plan_words(lengths.ctypes.data, len(lengths), meta.ctypes.data, capi.C.byref(got)))
+    assert got.value == n_tiles
+    return meta[: n_tiles * capi.TILE_WORDS], n_tiles
+
+
+def prepare_images(images) -> PreparedImages:
+    images = _cuda_f32(images, "images")
+    n_img = images.size(0)
+    out = torch.empty(n_img, capi.REGIONS, capi.EMBED, device=images.device, dtype=torch.bfloat16)
+    gram = torch.empty(n_img, capi.GRAM_TRI, device=images.device, dtype=torch.float32)
+    with torch.cuda.device(images.device):
+        check(capi.lib().itr_scan_prep_images_bf16(ptr(images), n_img, images.size(1), images.size(2), ptr(out), ptr(gram),
+                                                   stream_ptr()))
+    return PreparedImages(out, gram, n_img)
+
+
+def prepare_captions(captions, cap_lens, device=None) -> PreparedCaptions:
+    """captions: CUDA f32 tensor, or a PINNED host f32 tensor (read in place over PCIe: only the
+    true words of each caption cross the bus, not the zero padding)."""
+    if not isinstance(captions, torch.Tensor):
+        raise TypeError("captions must be a torch tensor")
+    if captions.is_cuda:
+        captions = _cuda_f32(captions, "captions")
+        device = captions.device
+    else:
+        if not captions.is_pinned() or captions.dtype != torch.float32 or not captions.is_contiguous():
+            raise RuntimeError("host captions must be a pinned, contiguous float32 tensor")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n_cap, lmax, d = captions.shape
+    ln = lengths_to_numpy(cap_lens, n_cap)
+    if n_cap and ln.max() > lmax:
+        raise ValueError("caption length {} exceeds the padded width {}".format(int(ln.max()), lmax))
+    meta_host, n_tiles = plan_words(ln)
+    meta = torch.from_numpy(meta_host).to(device, non_blocking=False)
+    rows = n_tiles * capi.TILE_WORDS
+    words = torch.empty(rows, capi.EMBED, device=device, dtype=torch.bfloat16)
+    wnorm = torch.empty(rows, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        check(capi.lib().itr_scan_pack_words_bf16(ptr(captions), n_cap, lmax, d, ptr(meta), n_tiles, ptr(words), ptr(wnorm),
+                                                  stream_ptr()))
+    return PreparedCaptions(words, meta, wnorm, n_tiles, n_cap, int(ln.sum()))
+
+
+def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, agg_func, lambda_softmax,
+                         lambda_lse, out=None):
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    dev = pi.images_bf16.device
+    if out is None:
+        out = torch.empty(pi.n_img, pc.n_cap, device=dev, dtype=torch.float32)
+    assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
+    with torch.cuda.device(dev):
+        check(capi.lib().itr_scan_t2i_scores_bf16(ptr(pi.images_bf16), ptr(pi.gram_tri), pi.n_img, ptr(pc.words_bf16),
+                                                  ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, norm, agg,
+                                                  float(lambda_softmax), float(lambda_lse), ptr(out),
+                                                  out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))
+    return out
+
+
+def scan_t2i_affinity_debug(pi: PreparedImages, pc: PreparedCaptions, word_tile, image_tile):
+    out = torch.empty(capi.TILE_WORDS, capi.TILE_IMAGES * capi.REGIONS, device=pi.images_bf16.device, dtype=torch.float32)
+    with torch.cuda.device(out.device):
+        check(capi.lib().itr_scan_t2i_affinity_debug(ptr(pi.images_bf16), pi.n_img, ptr(pc.words_bf16), pc.n_tiles,
+                                                     int(word_tile), int(image_tile), ptr(out), stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------ hinge
+def hinge(scores, margin, max_violation, need_grad=True):
+    scores = _cuda_f32(scores, "scores")
+    if scores.dim() != 2 or scores.size(0) != scores.size(1):
+        raise ValueError("the hinge loss needs a square score matrix, got {}".format(tuple(scores.shape)))
+    n = scores.size(0)
+    loss = torch.empty((), device=scores.device, dtype=torch.float32)
+    ds = torch.empty_like(scores) if need_grad else None
+    with torch.cuda.device(scores.device):
+        check(capi.lib().itr_hinge_fwd_bwd_f32(ptr(scores), scores.stride(0), n, float(margin), int(bool(max_violation)),
+                                               ptr(loss), ptr(ds), n, stream_ptr()))
+    return loss, ds
+
+
+def cosine_hinge(im, s, margin, max_violation, need_grad=True):
+    im, s = _cuda_f32(im, "im"), _cuda_f32(s, "s")
+    if im.shape != s.shape or im.dim() != 2:
+        raise ValueError("im and s must both be (batch, d), got {} and {}".format(tuple(im.shape), tuple(s.shape)))
+    n, d = im.shape
+    ws = torch.empty(2 * n * n, device=im.device, dtype=torch.float32)
+    loss = torch.empty((), device=im.device, dtype=torch.float32)
+    d_im = torch.empty_like(im) if need_grad else None
+    d_s = torch.empty_like(s) if need_grad else None
+    with torch.cuda.device(im.device):
+        check(capi.lib().itr_cosine_hinge_fwd_bwd_f32(ptr(im), ptr(s), n, d, float(margin), int(bool(max_violation)),
+                                                      ptr(ws), ptr(loss), ptr(d_im), ptr(d_s), stream_ptr()))
+    return loss, d_im, d_s
+
+
+# ------------------------------------------------------------------------------ ranking
+def rank_thresholds(scores, cap_offset=0, caps_per_img=5):
+    n_img, n_cap = scores.shape
+    thr_row = torch.empty(n_img, device=scores.device, dtype=torch.float32)
+    thr_col = torch.empty(n_cap, device=scores.device, dtype=torch.float32)
+    with torch.cuda.device(scores.device):
+        check(capi.lib().itr_rank_thresholds_f32(ptr(scores), scores.stride(0), n_img, n_cap, int(cap_offset),
+                                                 int(caps_per_img), ptr(thr_row), ptr(thr_col), stream_ptr()))
+    return thr_row, thr_col
+
+
+def rank_count(scores, thr_row, thr_col, cap_offset=0):
+    n_img, n_cap = scores.shape
+    dev = scores.device
+    cnt_row = torch.empty(n_img, device=dev, dtype=torch.int32)
+    cnt_col = torch.empty(n_cap, device=dev, dtype=torch.int32)
+    best_row = torch.empty(n_img, device=dev, dtype=torch.int64)
+    best_col = torch.empty(n_cap, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        check(capi.lib().itr_rank_count_f32(ptr(scores), scores.stride(0), n_img, n_cap, int(cap_offset), ptr(thr_row),
+                                            ptr(thr_col), ptr(cnt_row), ptr(cnt_col), ptr(best_row), ptr(best_col),
+                                            stream_ptr()))
+    return cnt_row, cnt_col, best_row, best_col
+
+
+def unpack_best_index(best):
+    """low 32 bits of the packed arg-max key hold ~index."""
+    return (~best) & 0xFFFFFFFF
+
+
+def rank_f64(sims, caps_per_img=5):
+    """sims: CUDA float64 (n_img, n_cap).  Returns (rank_row, rank_col, top1_row, top1_col) int32."""
+    assert sims.is_cuda and sims.dtype == torch.float64 and sims.stride(1) == 1
+    n_img, n_cap = sims.shape
+    outs = [torch.empty(n, device=sims.device, dtype=torch.int32) for n in (n_img, n_cap, n_img, n_cap)]
+    with torch.cuda.device(sims.device):
+        check(capi.lib().itr_rank_f64(ptr(sims), sims.stride(0), n_img, n_cap, int(caps_per_img), *[ptr(o) for o in outs],
+                                      stream_ptr()))
+    return tuple(outs)

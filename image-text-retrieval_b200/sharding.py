@@ -1,0 +1,111 @@
+"""Caption-sharded evaluation across the GPUs of one box.
+
+Every (image, caption) pair is independent, so the score matrix shards by caption blocks with
+no data-path collective: rank r owns a contiguous block of captions that starts on a multiple
+of ``caps_per_img`` (an image's ground-truth captions stay together), every rank holds all
+images.  Ranking needs one small exchange:
+
+  t2i  fully local -- a rank owns whole columns, so the rank and top-1 of its captions are exact;
+       the per-caption vectors are merged with one all-reduce (each rank contributes its slice).
+  i2t  the threshold of image i is its best ground-truth score, which lives on exactly one rank:
+       all-reduce(MAX) of a (n_img,) float vector; then every rank counts the local captions that
+       beat it and the counts are all-reduced (SUM); the global top-1 is an all-reduce(MAX) of a
+       packed (score, caption) key.
+
+All payloads are KBs, so the exchange is latency-bound; counts are integers, so the result is
+bit-identical for every world size.  ``torch.distributed`` (NCCL over NVLink on the box, gloo in
+the CPU tests) is plumbing only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+_SIGN = torch.iinfo(torch.int64).min
+
+
+def shard_bounds(n_cap: int, world_size: int, caps_per_img: int = 5):
+    """[(start, end)] caption ranges, contiguous, starting on multiples of caps_per_img, sizes
+    differing by at most one image's worth."""
+    groups = (n_cap + caps_per_img - 1) // caps_per_img
+    base, extra = divmod(groups, world_size)
+    out, g = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((min(g * caps_per_img, n_cap), min((g + n) * caps_per_img, n_cap)))
+        g += n
+    return out
+
+
+class CudaStats:
+    """Local block statistics from the CUDA rank kernels."""
+
+    @staticmethod
+    def thresholds(block, cap_offset, caps_per_img):
+        return ops.rank_thresholds(block, cap_offset, caps_per_img)
+
+    @staticmethod
+    def count(block, thr_row, thr_col, cap_offset):
+        cnt_row, cnt_col, best_row, best_col = ops.rank_count(block, thr_row, thr_col, cap_offset)
+        return cnt_row, cnt_col, best_row ^ _SIGN, ops.unpack_best_index(best_col)
+
+
+def _all_reduce(t, op, group):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=op, group=group)
+    return t
+
+
+def sharded_ranks(block, start, n_cap_total, group=None, caps_per_img=5, stats=CudaStats):
+    """block: this rank's (n_img, n_local) scores, first column = global caption ``start``.
+    Returns (i2t_ranks, i2t_top1, t2i_ranks, t2i_top1) as int64 tensors, identical on every rank.
+
+    best_row keys handed over by ``stats.count`` are signed-comparable int64 (unsigned key ^ 2^63)
+    whose low 32 bits hold ~(global caption index)."""
+    n_img, n_local = block.shape
+    dev = block.device
+    if n_local > 0:
+        thr_row, thr_col = stats.thresholds(block, start, caps_per_img)
+    else:
+        thr_row = torch.full((n_img,), float("-inf"), device=dev)
+        thr_col = torch.empty(0, device=dev)
+    thr_row = _all_reduce(thr_row.contiguous(), dist.ReduceOp.MAX, group)
+    merged = torch.zeros(n_img + 2 * n_cap_total, dtype=torch.int64, device=dev)
+    best = torch.full((n_img,), _SIGN, dtype=torch.int64, device=dev)
+    if n_local > 0:
+        cnt_row, cnt_col, best_row, best_col_idx = stats.count(block, thr_row, thr_col, start)
+        merged[:n_img] = cnt_row
+        merged[n_img + start: n_img + start + n_local] = cnt_col
+        merged[n_img + n_cap_total + start: n_img + n_cap_total + start + n_local] = best_col_idx
+        best = best_row.contiguous()
+    merged = _all_reduce(merged, dist.ReduceOp.SUM, group)
+    best = _all_reduce(best, dist.ReduceOp.MAX, group)
+    i2t_top1 = (~best) & 0xFFFFFFFF
+    return merged[:n_img], i2t_top1, merged[n_img: n_img + n_cap_total], merged[n_img + n_cap_total:]
+
+
+def sharded_scan_eval(images, captions_local, lengths_local, start, n_cap_total, config, group=None,
+                      caps_per_img=5, return_block=False):
+    """SCAN evaluation of this rank's caption block + the exchange.  images: all images (host numpy /
+    pinned or CUDA tensor); captions_local / lengths_local: this rank's block.  Returns the
+    reference's ``cal_recall`` dict (evaluation.py:225-259), identical on every rank."""
+    from . import evaluation as ev
+
+    class _M:                      # the two attributes device_sims reads from the model
+        sim_enc = None
+
+    m = _M()
+    m.config = config
+    from .objectives import ContrastiveLoss
+    m.criterion = ContrastiveLoss(config, margin=config.get("margin", 0), measure=config.get("measure", "cosine"),
+                                  max_violation=config.get("max_violation", False))
+    block = ev.device_sims(m, images, captions_local, lengths_local)
+    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in
+                  sharded_ranks(block, start, n_cap_total, group, caps_per_img)]
+    res = ev._recall_dict(ev._metrics(a), (a, b), ev._metrics(c), (c, d), verbose=False)
+    if return_block:
+        res["sims_block"] = block
+    return res

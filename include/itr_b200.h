@@ -1,0 +1,143 @@
+/*
+ * itr_b200 -- C ABI of the B200-native similarity / hinge-loss / Recall@K hot path.
+ *
+ * The reference (WangFei-2019/Image-text-Retrieval) is pure Python/PyTorch and has
+ * no FFI or plugin registry; its hot path is a handful of
+ * module-level Python functions.  This header is the native boundary underneath the
+ * Python drop-ins for those functions: each entry point below names the reference
+ * function (file:line, relative to the reference root) whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every `const T*` / `T*` is a DEVICE pointer unless the
+ *     parameter name ends in `_host`; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream); all launches are asynchronous on `stream`.
+ *   - matrices are row-major; `ld_*` are leading dimensions in ELEMENTS.
+ *   - return value: ITR_OK, or an ITR_ERR_* code with a message in itr_last_error()
+ *     (thread-local).  No entry point falls back to the CPU.
+ *   - bf16 buffers are passed as `uint16_t*` (raw bit patterns).
+ */
+#ifndef ITR_B200_H_
+#define ITR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITR_OK               0
+#define ITR_ERR_INVALID      1   /* bad argument / unsupported mode  -> ValueError   */
+#define ITR_ERR_CUDA         2   /* CUDA runtime or driver error     -> RuntimeError */
+#define ITR_ERR_UNSUPPORTED  3   /* device is not sm_100             -> RuntimeError */
+
+/* config['cross_attn'], Objectives.py:64-71 */
+#define ITR_T2I 0
+#define ITR_I2T 1
+/* config['raw_feature_norm'], Objectives.py:436-457 (the l1 modes raise NameError upstream, defect D4) */
+#define ITR_NORM_CLIPPED_L2 0
+#define ITR_NORM_L2         1
+#define ITR_NORM_SOFTMAX    2
+#define ITR_NORM_CLIPPED    3
+#define ITR_NORM_NONE       4
+/* config['agg_func'], Objectives.py:355-366 */
+#define ITR_AGG_LSE  0
+#define ITR_AGG_MEAN 1
+#define ITR_AGG_MAX  2
+#define ITR_AGG_SUM  3
+
+#define ITR_REGIONS        36    /* precomp regions per image the tensor-core path is built for */
+#define ITR_EMBED          1024  /* embed_size, itr/config.py:73 */
+#define ITR_TILE_WORDS     128   /* rows of one packed word tile (= UMMA M) */
+#define ITR_TILE_IMAGES    4     /* images per accumulator tile (UMMA N = 4*36 = 144) */
+#define ITR_GRAM_TRI       720   /* floats per image of the packed lower-triangular region Gram */
+#define ITR_MAX_WORDS_F32  80    /* longest caption the fp32 validation kernel accepts */
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* itr_last_error(void);
+int         itr_version(void);
+/* 1 if `device` is compute capability 10.x, 0 if not, negative ITR_ERR_* on error */
+int         itr_device_supported(int device);
+
+/* ---- VSE++ scores: cosine_sim(im, s), Objectives.py:18-21 ------------------------------
+ * scores[i, c] = sum_d im[i, d] * s[c, d]   (inputs already unit-norm; fp32 FMA, 1e-5 mode) */
+int itr_cosine_scores_f32(const float* im, const float* s, int n_img, int n_cap, int d,
+                          float* scores, int64_t ld_scores, void* stream);
+
+/* ---- SCAN scores, float32 validation mode ---------------------------------------------
+ * xattn_score_t2i / xattn_score_i2t + func_attention + cosine_similarity,
+ * Objectives.py:329-372, 376-417, 421-476, 10-15; l2norm utils.py:11-15.
+ * All five working raw_feature_norm modes x four agg_func x both directions.
+ * images (n_img, n_regions, d); captions (n_cap, lmax, d) zero padded; cap_lens (n_cap).
+ * gram: (n_img, n_regions, n_regions) from itr_region_gram_f32 (needed for ITR_T2I; may be NULL for ITR_I2T). */
+int itr_region_gram_f32(const float* images, int n_img, int n_regions, int d, float* gram, void* stream);
+int itr_scan_scores_f32(const float* images, const float* gram, const float* captions, const int32_t* cap_lens,
+                        int n_img, int n_regions, int n_cap, int lmax, int d,
+                        int cross_attn, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
+                        float* scores, int64_t ld_scores, void* stream);
+
+/* ---- SCAN t2i scores, tcgen05 tensor-core path (bf16 inputs, fp32 accumulate) ----------
+ * Same function as above for cross_attn = t2i, raw_feature_norm in {clipped_l2norm, l2norm}.
+ *
+ * 1. itr_scan_plan_words (HOST, no CUDA): bin-packs captions into 128-row word tiles so that
+ *    no caption of <= 32 words straddles a 32-row quarter; longer captions get a tile of
+ *    their own.  Output, per packed row: row_meta[4*row + {0,1,2,3}] =
+ *      { caption id (-1 = padding), word index, seg_lo | seg_hi<<8 | long_tile<<16, caption length }.
+ *    Returns the number of tiles through *n_tiles; arrays must hold itr_scan_plan_max_tiles() tiles.
+ * 2. itr_scan_pack_words_bf16: gathers the words (captions may live in device memory or in
+ *    pinned host memory mapped into the device address space), rounds to bf16 and writes each
+ *    row's L2 norm (of the rounded values).
+ * 3. itr_scan_prep_images_bf16: rounds regions to bf16 and writes the packed lower-triangular
+ *    36x36 Gram matrix of the rounded regions (diagonal pre-halved), ITR_GRAM_TRI floats per image.
+ * 4. itr_scan_t2i_scores_bf16: persistent TMA -> tcgen05.mma -> TMEM epilogue kernel.
+ */
+int itr_scan_plan_max_tiles(const int32_t* cap_lens_host, int n_cap);
+int itr_scan_plan_words(const int32_t* cap_lens_host, int n_cap, int32_t* row_meta_host, int* n_tiles);
+int itr_scan_pack_words_bf16(const float* captions, int n_cap, int lmax, int d,
+                             const int32_t* row_meta, int n_tiles,
+                             uint16_t* words_bf16, float* row_wnorm, void* stream);
+int itr_scan_prep_images_bf16(const float* images, int n_img, int n_regions, int d,
+                              uint16_t* images_bf16, float* gram_tri, void* stream);
+int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const float* gram_tri, int n_img,
+                             const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                             int n_tiles, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
+                             float* scores, int64_t ld_scores, void* stream);
+/* Debug / bring-up: raw region-word affinities of ONE (word tile, image tile) pair as the
+ * tensor cores produced them: out[128 rows][144 cols] fp32. */
+int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,
+                                int word_tile, int image_tile, float* out, void* stream);
+
+/* ---- hinge loss: ContrastiveLoss.forward / TripletLoss.forward, Objectives.py:93-115, 492-517
+ * loss (1 float, device) = sum of both directions; dscores (n x n, may be NULL) = dloss/dscores. */
+int itr_hinge_fwd_bwd_f32(const float* scores, int64_t ld_scores, int n, float margin, int max_violation,
+                          float* loss, float* dscores, int64_t ld_dscores, void* stream);
+/* VSE++ training step of the path: scores = im @ s.T, hinge, and the gradients w.r.t. both
+ * embedding matrices (d_im = dS @ s, d_s = dS.T @ im).  ws: n*n*2 floats of workspace. */
+int itr_cosine_hinge_fwd_bwd_f32(const float* im, const float* s, int n, int d, float margin, int max_violation,
+                                 float* ws, float* loss, float* d_im, float* d_s, void* stream);
+
+/* ---- ranking: i2t / t2i, evaluation.py:156-189, 192-222 ---------------------------------
+ * Works on a column block [n_img x n_cap_local] of the full matrix whose first column is global
+ * caption `cap_offset` (a multiple of caps_per_img), so caption shards rank locally.
+ *   thr_col[c]  = score of caption c's ground-truth image  (global image (cap_offset+c)/caps_per_img)
+ *   thr_row[i]  = best score among image i's ground-truth captions inside this block (-inf if none)
+ *   cnt_row[i]  = #{c : scores[i,c] > thr_row[i]}        cnt_col[c] = #{i : scores[i,c] > thr_col[c]}
+ *   best_row[i] / best_col[c] = arg-max packed as (orderable score bits << 32) | ~index
+ * With one block, rank_i2t = cnt_row and rank_t2i = cnt_col (position among strictly greater scores).
+ * Multi-GPU: all-reduce MAX thr_row, run the count pass, all-reduce SUM cnt_row / MAX best_row. */
+int itr_rank_thresholds_f32(const float* scores, int64_t ld_scores, int n_img, int n_cap_local,
+                            int cap_offset, int caps_per_img, float* thr_row, float* thr_col, void* stream);
+int itr_rank_count_f32(const float* scores, int64_t ld_scores, int n_img, int n_cap_local, int cap_offset,
+                       const float* thr_row, const float* thr_col,
+                       int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col, void* stream);
+
+/* float64 variant for a whole host-provided matrix (i2t(sims) / t2i(sims) take the float64
+ * array cal_sims returns, evaluation.py:140,156,192): ranks (strictly-greater counts) and the
+ * arg-max (lowest index on ties) of every row and every column. */
+int itr_rank_f64(const double* scores, int64_t ld_scores, int n_img, int n_cap, int caps_per_img,
+                 int32_t* rank_row, int32_t* rank_col, int32_t* top1_row, int32_t* top1_col, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITR_B200_H_ */
