@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], the config the metric is quoted on; it fits one GPU):
+SCAN t2i, clipped_l2norm, LogSumExp (lambda_lse 6, lambda_softmax 9), COCO-5K shape =
+5000 images x 25000 captions (312 906 words), synthetic embeddings.
+One step = one full evaluation pass: fp32 embeddings -> bf16 prep (cast, pack, Grams) ->
+tcgen05 score kernel -> rank kernels (-> the tiny rank exchange when N > 1).  The captions are
+sharded across ranks (strong scaling: the total problem is fixed).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the
+same metric through the public API (itr_b200.sharding.sharded_scan_eval, the multi-GPU form of
+cal_sims + cal_recall) with pinned HOST buffers, copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG = dict(name="SCAN", cross_attn="t2i", raw_feature_norm="clipped_l2norm", agg_func="LogSumExp",
+              lambda_lse=6.0, lambda_softmax=9.0, margin=0.2, max_violation=True, measure="cosine")
+METRIC = "image-caption pair scores/sec (SCAN t2i COCO-5K eval)"
+R, D = 36, 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-img", type=int, default=5000, help="override for debugging only (invalidates the number)")
+    ap.add_argument("--n-cap", type=int, default=25000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-caps", type=int, default=300)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured (sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.file = index, None, None
+
+    def start(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [l.strip().split(", ") for l in open(self.file.name) if l.strip()]
+        os.unlink(self.file.name)
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+_CPU_INPUTS = {}
+
+
+def cpu_port_rate(n_img_s, n_cap_s, seed=14, lam=10.5, repeats=1):
+    """The oracle's float32 torch-CPU port (same per-caption loop as the reference) on a bounded
+    sample of the workload: first n_img_s images x first n_cap_s captions.  Returns (pairs/s, seconds, cores)."""
+    from itr_b200 import synth
+    from oracle import ref_port
+    if (n_img_s, n_cap_s) not in _CPU_INPUTS:
+        lengths = synth.caption_lengths(25000, lam, seed)[:n_cap_s]
+        _CPU_INPUTS[(n_img_s, n_cap_s)] = synth.scan_inputs(n_img_s, n_cap_s, lam, seed, device="cpu", lengths=lengths)
+    img, cap, ln = _CPU_INPUTS[(n_img_s, n_cap_s)]
+    cores = torch.get_num_threads()
+    ref_port.scan_scores(img[:8], cap[:4], ln[:4], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)   # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        s = ref_port.scan_scores(img, cap, ln, "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+        sims = s.double().numpy()
+        # the reference then ranks on the host; time it on the sample's square part
+        m = min(n_img_s, n_cap_s // 5)
+        if m >= 1:
+            ref_port.i2t_ranks(sims[:m, : 5 * m]); ref_port.t2i_ranks(sims[:m, : 5 * m])
+        best = min(best, time.perf_counter() - t0)
+    return n_img_s * n_cap_s / best, best, cores
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference is absent on the GPU
+    box and is pure Python, so there is nothing to compile) on this box's host cores."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_img_s, n_cap_s = min(1000, args.n_img), min(args.cpu_sample_caps // 3, args.n_cap)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, secs, cores = cpu_port_rate(n_img_s, n_cap_s)
+        if i >= args.warmup:
+            times.append(secs)
+        if i == 0 and secs * (args.warmup + args.steps) > 240:      # keep the whole run within minutes
+            n_cap_s = max(10, int(n_cap_s * 240 / (secs * (args.warmup + args.steps))))
+    t = float(np.mean(times))
+    value = n_img_s * n_cap_s / t
+    sample = "first {} images x first {} captions of the COCO-5K-shaped workload per step, fp32 torch CPU".format(n_img_s, n_cap_s)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SCAN t2i LSE COCO-5K shape (5000 img x 25000 caps); CPU arm scores a bounded sample per step",
+                       "n_img": args.n_img, "n_cap": args.n_cap},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import itr_b200
+    from itr_b200 import evaluation as ev, ops, sharding, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ synthetic workload
+    n_img, n_cap = args.n_img, args.n_cap
+    lengths = synth.caption_lengths(n_cap, 10.5, 14)
+    lo, hi = sharding.shard_bounds(n_cap, world)[rank]
+    images, captions, _ = synth.scan_inputs(n_img, n_cap, 10.5, 14, device=dev, lengths=lengths)
+    captions = captions[lo:hi].contiguous()
+    ln_local = lengths[lo:hi]
+    sum_words, sum_words_local = int(lengths.sum()), int(ln_local.sum())
+    torch.cuda.synchronize()
+
+    scores = torch.empty(n_img, hi - lo, device=dev, dtype=torch.float32)
+    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_end = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        pi = ops.prepare_images(images)
+        pc = ops.prepare_captions(captions, ln_local)
+        if i is not None:
+            k_start[i].record()
+        ops.scan_t2i_scores_bf16(pi, pc, CONFIG["raw_feature_norm"], CONFIG["agg_func"], CONFIG["lambda_softmax"],
+                                 CONFIG["lambda_lse"], out=scores)
+        if i is not None:
+            k_end[i].record()
+        return sharding.sharded_ranks(scores, lo, n_cap, None, 5)
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        out = step(i)
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    kern_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in zip(k_start, k_end)]))], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = elapsed_ms.item() / args.steps
+    value = n_img * n_cap / (ms_per_step * 1e-3)
+    i2t_ranks, _, t2i_ranks, _ = out
+    r1 = 100.0 * (i2t_ranks < 1).float().mean().item()
+    r1_t = 100.0 * (t2i_ranks < 1).float().mean().item()
+
+    # ------------------------------------------------------------------ end to end, host buffers
+    images_h = torch.empty(images.shape, dtype=torch.float32, pin_memory=True).copy_(images)
+    captions_h = torch.empty(captions.shape, dtype=torch.float32, pin_memory=True).copy_(captions)
+    del captions
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        return sharding.sharded_scan_eval(images_h, captions_h, ln_local, lo, n_cap, CONFIG, None)
+
+    for _ in range(min(args.warmup, 2)):
+        res = e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - w0) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = n_img * n_cap / e2e_s.item()
+    n_tiles = ops.plan_words(ln_local)[1]
+    h2d = n_img * R * D * 4 + sum_words_local * D * 4 + n_tiles * 128 * 16
+    d2h = (n_img * 2 + n_cap * 2) * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    f_alg = 2.0 * R * D * sum_words_local * n_img            # true words, affinity contraction only
+    achieved = f_alg / (kern_ms.item() * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "SCAN t2i clipped_l2norm LogSumExp (lambda_lse 6, lambda_softmax 9), COCO-5K shape: "
+                               "{} images x {} captions ({} words), captions sharded over {} GPU(s)".format(n_img, n_cap, sum_words, world),
+                   "n_img": n_img, "n_cap": n_cap, "sum_words": sum_words, "parallelism": "caption-shard x{}".format(world),
+                   "l2_policy": "inputs larger than L2 (bf16 operands {:.0f} MB + {:.0f} MB score block per GPU)".format(
+                       (n_img * R * D * 2 + n_tiles * 128 * D * 2) / 1e6, n_img * (hi - lo) * 4 / 1e6),
+                   "step": "prep(cast,pack,gram) + tcgen05 scores + rank kernels" + (" + rank exchange" if world > 1 else "")},
+        "eval_wall_ms": {"device": ms_per_step, "e2e": e2e_s.item() * 1e3},
+        "recall_check": {"i2t_r1": r1, "t2i_r1": r1_t, "e2e_rsum": res["rsum"]},
+        "roofline": {"bound": "tensor", "kernel": "scan_t2i_tc_kernel", "achieved": achieved, "peak": pk["tflops"],
+                     "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                     "kernel_ms": kern_ms.item(), "algorithmic_flop_per_launch": f_alg,
+                     "kernel_share_of_step": kern_ms.item() / ms_per_step},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s.item() * 1e3},
+        "gpu_launches": 5 * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_s, c_s = min(1000, n_img), min(args.cpu_sample_caps, n_cap)
+        rate, secs, cores = cpu_port_rate(n_s, c_s)
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": "first {} images x first {} captions of the same workload, fp32 torch CPU port of "
+                                          "the reference's per-caption loop + numpy ranking, {:.1f} s".format(n_s, c_s, secs)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+"""GPU parity of the float32 kernels (1e-5 mode) against the oracle and the golden fixtures,
+called through the Python drop-ins, i.e. through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits_to_f32, load_golden
+import itr_b200
+from itr_b200 import evaluation as ev, objectives as ob, ops
+from oracle import scan_oracle as so
+
+pytestmark = pytest.mark.gpu
+RTOL32, ATOL32 = 1e-5, 2e-6      # "1e-5 in an fp32 mode" (BASELINE.json north_star)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def cfg(**kw):
+    base = dict(name="SCAN", cross_attn="t2i", raw_feature_norm="clipped_l2norm", agg_func="LogSumExp",
+                lambda_lse=6.0, lambda_softmax=9.0, margin=0.2, max_violation=True, measure="cosine",
+                itr_b200_precision="fp32")
+    base.update(kw)
+    return base
+
+
+class FakeModel:
+    sim_enc = None
+
+    def __init__(self, config):
+        self.config = config
+        self.criterion = ob.ContrastiveLoss(config, margin=config["margin"], measure=config["measure"],
+                                            max_violation=config["max_violation"])
+
+
+def test_library_sees_sm100():
+    assert ops.capi.lib().itr_device_supported(0) == 1
+
+
+def test_cosine_golden_and_odd_shapes():
+    g = load_golden("vse_hinge")
+    im, s = bits_to_f32(g["im_bits"]), bits_to_f32(g["s_bits"])
+    got = ob.cosine_sim(dev(im), dev(s)).cpu().numpy()
+    np.testing.assert_allclose(got, g["cosine|f64"], rtol=RTOL32, atol=ATOL32)
+    rng = np.random.default_rng(0)
+    for n_img, n_cap, d in [(1, 1, 1), (37, 53, 100), (130, 65, 1024), (64, 64, 17)]:
+        a = rng.standard_normal((n_img, d)).astype(np.float32)
+        b = rng.standard_normal((n_cap, d)).astype(np.float32)
+        ref = so.cosine_scores(a, b)
+        got = ob.cosine_sim(dev(a), dev(b)).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=RTOL32, atol=1e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", ["scan_small", "scan_long"])
+@pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
+def test_scan_f32_golden_all_modes(case, direction, lam_sm):
+    g = load_golden(case)
+    img, cap, lens = dev(bits_to_f32(g["img_bits"])), dev(bits_to_f32(g["cap_bits"])), g["lens"]
+    fn = ob.xattn_score_t2i if direction == "t2i" else ob.xattn_score_i2t
+    for norm in so.RAW_FEATURE_NORMS:
+        for agg in so.AGG_FUNCS:
+            c = cfg(cross_attn=direction, raw_feature_norm=norm, agg_func=agg, lambda_softmax=lam_sm)
+            got = fn(img, cap, lens.tolist(), c).cpu().numpy()
+            want = g["{}|{}|{}|f64".format(direction, norm, agg)]
+            np.testing.assert_allclose(got, want, rtol=RTOL32, atol=ATOL32, err_msg="{} {} {}".format(direction, norm, agg))
+
+
+def test_scan_f32_vs_oracle_ragged_and_padding_invariance():
+    img, cap, lens = itr_b200.synth.scan_inputs(13, 27, 10.5, 5)
+    lens = lens.copy(); lens[:4] = [1, 2, 80 if cap.size(1) >= 80 else cap.size(1), 3]
+    lens = np.minimum(lens, cap.size(1))
+    for direction, lam in (("t2i", 9.0), ("i2t", 4.0)):
+        want = so.scan_scores(img.numpy(), cap.numpy(), lens, direction, "clipped_l2norm", "LogSumExp", lam, 6.0)
+        fn = ob.xattn_score_t2i if direction == "t2i" else ob.xattn_score_i2t
+        c = cfg(cross_attn=direction, lambda_softmax=lam)
+        got = fn(img.cuda(), cap.cuda(), lens, c).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=RTOL32, atol=ATOL32)
+        # words beyond len must not matter (the reference slices them away, Objectives.py:341)
+        dirty = cap.clone()
+        for k, n in enumerate(lens):
+            dirty[k, n:] = 7.0
+        got2 = fn(img.cuda(), dirty.cuda(), torch.from_numpy(lens), c).cpu().numpy()
+        np.testing.assert_array_equal(got, got2)
+
+
+def test_scan_aggregation_ordering_property():
+    img, cap, lens = itr_b200.synth.scan_inputs(20, 40, 10.5, 9)
+    out = {}
+    for agg in so.AGG_FUNCS:
+        out[agg] = ob.xattn_score_t2i(img.cuda(), cap.cuda(), lens, cfg(agg_func=agg)).cpu().numpy()
+    n = lens[None, :].astype(np.float64)
+    assert (out["LogSumExp"] >= out["Max"] - 1e-6).all()           # lse_lambda >= max
+    assert (out["Max"] >= out["Mean"] - 1e-6).all()
+    np.testing.assert_allclose(out["Sum"], out["Mean"] * n, rtol=1e-5, atol=1e-6)
+    assert (out["LogSumExp"] <= out["Max"] + np.log(n) / 6.0 + 1e-6).all()
+
+
+def test_hinge_golden_and_autograd():
+    g = load_golden("vse_hinge")
+    im, s = dev(bits_to_f32(g["im_bits"])), dev(bits_to_f32(g["s_bits"]))
+    for margin in (0.0, 0.2):
+        for mv in (False, True):
+            key = "hinge|m{}|mv{}".format(margin, int(mv))
+            # TripletLoss on a ready matrix
+            sc = dev(g["cosine|f64"].astype(np.float32)).requires_grad_(True)
+            loss = ob.TripletLoss(margin=margin, max_violation=mv)(sc)
+            loss.backward()
+            np.testing.assert_allclose(loss.item(), g[key + "|loss"], rtol=2e-5)
+            np.testing.assert_array_equal(sc.grad.cpu().numpy(), g[key + "|dscores"])
+            # ContrastiveLoss (VSE++): fused scores + hinge + embedding gradients
+            a, b = im.clone().requires_grad_(True), s.clone().requires_grad_(True)
+            crit = ob.ContrastiveLoss(cfg(name="VSE++"), margin=margin, measure="cosine", max_violation=mv)
+            l2 = crit(a, b)
+            (2.0 * l2).backward()
+            np.testing.assert_allclose(l2.item(), g[key + "|loss"], rtol=2e-5)
+            np.testing.assert_allclose(a.grad.cpu().numpy(), 2.0 * g[key + "|d_im"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(b.grad.cpu().numpy(), 2.0 * g[key + "|d_s"], rtol=1e-5, atol=1e-6)
+            # SGRAF calling style: the matrix arrives as `im`
+            sc2 = sc.detach().clone().requires_grad_(True)
+            l3 = ob.ContrastiveLoss(cfg(name="SGRAF"), margin=margin, measure="cosine", max_violation=mv)(sc2)
+            l3.backward()
+            np.testing.assert_array_equal(sc2.grad.cpu().numpy(), g[key + "|dscores"])
+
+
+def test_hinge_batch128_vs_oracle_and_properties():
+    im, s = itr_b200.synth.vse_inputs(128, 640, 2)
+    s = s[::5].contiguous()
+    sc = so.cosine_scores(im.numpy(), s.numpy())
+    for mv in (True, False):
+        want, dwant = so.hinge_loss(sc, 0.2, mv)
+        a = im.cuda().requires_grad_(True); b = s.cuda().requires_grad_(True)
+        loss = ob.ContrastiveLoss(cfg(name="VSE++"), margin=0.2, measure="cosine", max_violation=mv)(a, b)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), want, rtol=1e-4)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), dwant @ s.numpy().astype(np.float64), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(b.grad.cpu().numpy(), dwant.T @ im.numpy().astype(np.float64), rtol=1e-4, atol=1e-5)
+    # margin satisfied everywhere -> zero loss, zero gradient
+    big = torch.eye(16, device="cuda") * 5.0
+    big.requires_grad_(True)
+    l = ob.TripletLoss(margin=0.2, max_violation=True)(big)
+    l.backward()
+    assert l.item() == 0.0 and big.grad.abs().sum().item() == 0.0
+    # single pair: no negatives
+    one = torch.ones(1, 1, device="cuda", requires_grad=True)
+    assert ob.TripletLoss(margin=0.2, max_violation=True)(one).item() == 0.0
+
+
+def test_ranking_golden_f64_and_f32():
+    g = load_golden("ranking")
+    sims = g["sims"]
+    (m, (ranks, top1)) = ev.i2t(sims, return_ranks=True)
+    np.testing.assert_array_equal(ranks, g["i2t_ranks"]); np.testing.assert_array_equal(top1, g["i2t_top1"])
+    np.testing.assert_allclose(m, g["i2t_metrics"])
+    (mi, (ranks_i, top1_i)) = ev.t2i(sims, return_ranks=True)
+    np.testing.assert_array_equal(ranks_i, g["t2i_ranks"]); np.testing.assert_array_equal(top1_i, g["t2i_top1"])
+    np.testing.assert_allclose(mi, g["t2i_metrics"])
+    rd = ev.cal_recall(sims, verbose=False)
+    np.testing.assert_allclose(rd["result"], g["result"]); np.testing.assert_allclose(rd["rsum"], g["rsum"])
+    assert sorted(rd) == sorted(so.recall_dict(sims))
+    assert rd["i2t_ranks"].dtype == np.float64 and rd["t2i_top1"].dtype == np.float64
+    assert ev.i2t(sims) == m                       # return_ranks=False form
+    # float32 device path on a non-square-block shape, incl. exact ties (rank = strictly greater count)
+    rng = np.random.default_rng(1)
+    s32 = rng.standard_normal((301, 1505)).astype(np.float32)
+    s32[5, 100] = s32[5, 25]                      # tie with a ground-truth score
+    a, b, c, d = [x.cpu().numpy() for x in ev.device_ranks(dev(s32))]
+    ia, ic, _, _ = so.strict_ranks(s32)
+    np.testing.assert_array_equal(a, ia); np.testing.assert_array_equal(c, ic)
+    np.testing.assert_array_equal(b, s32.argmax(1)); np.testing.assert_array_equal(d, s32.argmax(0))
+    # and where nothing ties, it equals the reference's argsort positions
+    ref_i, ref_c = so.rank_i2t(s32.astype(np.float64))[1], so.rank_t2i(s32.astype(np.float64))[1]
+    ok_i = np.ones(301, bool); ok_i[5] = False
+    np.testing.assert_array_equal(a[ok_i], ref_i[ok_i]); np.testing.assert_array_equal(c, ref_c)
+
+
+def test_cal_sims_dropin_vse_and_scan_fp32():
+    im, s = itr_b200.synth.vse_inputs(40, 200, 4)
+    model = FakeModel(cfg(name="VSE++"))
+    sims = ev.cal_sims(model, im.numpy(), s.numpy(), shard_size=64)
+    assert sims.dtype == np.float64 and sims.shape == (40, 200)
+    np.testing.assert_allclose(sims, so.cosine_scores(im.numpy(), s.numpy()), rtol=RTOL32, atol=ATOL32)
+    res = ev.cal_sims_and_recall(model, im.numpy(), s.numpy())
+    want = so.recall_dict(sims)
+    for k in ("i2t_ranks", "t2i_ranks", "i2t_top1", "t2i_top1"):
+        np.testing.assert_array_equal(res[k], want[k])
+    np.testing.assert_allclose(res["result"], want["result"])
+    # SCAN i2t Mean (config 4 style) through cal_sims, fp32 mode, plus the defect-D1 compat switch
+    img, cap, lens = itr_b200.synth.scan_inputs(12, 60, 10.5, 11)
+    c = cfg(cross_attn="i2t", agg_func="Mean", lambda_softmax=4.0)
+    model = FakeModel(c)
+    got = ev.cal_sims(model, img.numpy(), cap.numpy(), lens, shard_size=25)
+    want = so.scan_scores(img.numpy(), cap.numpy(), lens, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+    np.testing.assert_allclose(got, want, rtol=RTOL32, atol=ATOL32)
+    compat = ev.cal_sims(model, img.numpy(), cap.numpy(), lens, shard_size=25, compat_unsliced_lengths=True)
+    lens_d1 = np.minimum(lens[np.arange(60) % 25], cap.size(1))
+    want_d1 = so.scan_scores(img.numpy(), cap.numpy(), lens_d1, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+    np.testing.assert_allclose(compat, want_d1, rtol=RTOL32, atol=ATOL32)
