@@ -21,13 +21,26 @@
 //   warp 0     TMA producer: 5-stage ring of {words 128x64, regions 144x64} bf16 tiles, SWIZZLE_128B,
 //              plus per-tile aux data (4 packed Grams, row metadata, word norms) by bulk copy
 //   warp 1     tcgen05.mma issuer (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM)
-//   warp 2     TMEM allocator (2 accumulator buffers of 144 columns)
-//   warps 4-11 epilogue: thread = one word row; tcgen05.ld its 36 columns per image, then the
-//              whole softmax / cosine / aggregation chain in registers; the two cross-row
-//              reductions (l2norm over the caption's words, aggregation over words) are
-//              segmented warp scans -- itr_scan_plan_words guarantees a caption never
+//   warp 2     TMEM allocator (2 accumulator buffers of 144 columns + 4 Gram-product buffers)
+//   warps 2,3  issuers of the small "Gram" MMAs (one per epilogue group, see below)
+//   warps 4-11 epilogue, two groups of four warps; a group owns two of the tile's four images and
+//              all 128 word rows (thread = one word row = one TMEM lane):
+//                phase A(image): tcgen05.ld the 36 raw affinities -> leaky, l2norm over the
+//                  caption's words (segmented warp scan), e_k = exp2(lambda*ahat_k - lambda) in
+//                  registers; e is also written back, as fp16, over the image's now dead
+//                  accumulator columns (tcgen05.st) and a warp 2/3 thread issues
+//                  U = e . G_offdiag as a 128x48x48 tcgen05.mma with A FROM TMEM and the image's
+//                  fp16 Gram as the SMEM B operand;
+//                phase B(image): tcgen05.ld U, |ctx|^2 Z^2 = sum_k e_k U_k + sum_k G_kk e_k^2
+//                  (diagonal kept in fp32), cosine, aggregation over the caption's words.
+//              A(0) A(1) B(0) B(1) are software-pipelined so the Gram MMA latency is hidden.
+//              The two cross-row reductions (l2norm over the caption's words, aggregation over
+//              words) are segmented warp scans -- itr_scan_plan_words guarantees a caption never
 //              straddles a warp, except in `long` tiles which exchange through shared memory.
+// v1 of this kernel evaluated e^T G e on the CUDA cores from a broadcast SMEM copy of G: ncu showed
+// the SMEM data pipe 77% busy and the tensor pipe 22% (profiles/r01/ncu_v1_summary.txt).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -46,13 +59,20 @@ constexpr int STAGES = 5;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2; // 16384
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2; // 18432
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GRAM_FLOATS = ITR_GRAM_TRI;      // 720 per image
-constexpr int AUX_GRAM = IMGS * GRAM_FLOATS * 4;   // 11520
+// per-image Gram pack: fp16 48x48 off-diagonal Gram in the canonical no-swizzle K-major UMMA layout
+// (8x8 core matrices of 128 bytes; element (n,k) at (n/8)*768 + (k/8)*128 + (n%8)*16 + (k%8)*2),
+// followed by the 36 fp32 diagonal entries.
+constexpr int GRAM_N = 48;
+constexpr int G16_BYTES = GRAM_N * GRAM_N * 2;     // 4608
+constexpr int GRAM_BYTES = ITR_GRAM_BYTES;         // 4752 = 4608 + 36*4
+constexpr int G_LBO = 128, G_SBO = 768;
+constexpr int AUX_GRAM = IMGS * GRAM_BYTES;        // 19008
 constexpr int AUX_META = BLOCK_M * 16;             // 2048
 constexpr int AUX_WNORM = BLOCK_M * 4;             // 512
-constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 14080
-constexpr int XCH_FLOATS = 2 /*half*/ * 2 /*image*/ * 4 /*warp*/ * 40;
-constexpr int ACC_COLS = 256;                  // column stride between the two accumulators
+constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 21568
+constexpr int XCH_FLOATS = 2 /*group*/ * 2 /*image*/ * 4 /*warp*/ * 40;
+constexpr int ACC_COLS = 144;                  // column stride between the two accumulators
+constexpr int U_BASE = 288;                    // four 48-column Gram-product buffers: [288, 480)
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 32;                       // word tiles kept L2-resident while images stream
 constexpr int NUM_THREADS = 384;
@@ -63,13 +83,15 @@ constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_XCH = SMEM_AUX + 2 * AUX_BYTES;
 constexpr int SMEM_BARS = SMEM_XCH + XCH_FLOATS * 4;
-constexpr int NUM_BARS = 2 * STAGES + 8;
+constexpr int NUM_BARS = 2 * STAGES + 16;
 constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for manual 1024-byte alignment
 
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=144
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// Gram MMA: D=f32, A=B=fp16, K-major, M=128, N=48
+constexpr uint32_t IDESC_GRAM = (1u << 4) | ((uint32_t)(GRAM_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,20 +105,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+// try_wait suspends the thread in hardware until the phase completes or ~`hint_ns` elapse
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hang.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity, 20000u)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait(bar, parity, 20000u)) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
@@ -117,12 +140,39 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// A operand read from tensor memory (lanes = M rows, two fp16 K elements per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // K-major, SWIZZLE_128B operand tile whose rows are 128 bytes: 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// K-major, no swizzle: 8x8 core matrices, LBO = stride between core matrices along K, SBO = along N
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+#define TMEM_ST_X16(taddr, v, o)                                                                                     \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]),  \
+                 "r"(v[o + 6]), "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]),            \
+                 "r"(v[o + 12]), "r"(v[o + 13]), "r"(v[o + 14]), "r"(v[o + 15]) : "memory")
+#define TMEM_ST_X8(taddr, v, o)                                                                     \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"             \
+               ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), \
+                 "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7]) : "memory")
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 #define TMEM_LD_X32(taddr, v, o)                                                                                       \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"        \
@@ -138,6 +188,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"           \
                : "=f"(v[o + 0]), "=f"(v[o + 1]), "=f"(v[o + 2]), "=f"(v[o + 3])       \
                : "r"(taddr))
+#define TMEM_LD_X16U(taddr, v, o)                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),      \
+                 "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),    \
+                 "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                   \
+               : "r"(taddr))
+#define TMEM_LD_X8U(taddr, v, o)                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"             \
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]),    \
+                 "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])                                     \
+               : "r"(taddr))
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -173,7 +237,7 @@ struct Schedule {
 };
 
 struct Params {
-  const float* gram_tri;       // [n_img][720]
+  const uint8_t* gram_pack;    // [n_img][GRAM_BYTES]
   const int4* row_meta;        // [n_wt*128]
   const float* row_wnorm;      // [n_wt*128]
   int n_img, n_wt, n_it;
@@ -197,6 +261,10 @@ __device__ __forceinline__ float seg_total(float x, const bool (&p)[5], int seg_
   return __shfl_sync(0xffffffffu, x, seg_hi);
 }
 
+// column offset (inside an accumulator buffer) where image i's fp16 softmax numerators are parked:
+// 16-column aligned and inside the image's own 36 columns [36 i, 36 i + 36)
+__device__ __forceinline__ int e_col(int i) { return i == 0 ? 0 : 16 + 32 * i; }   // 0, 48, 80, 112
+
 template <bool DEBUG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
@@ -212,6 +280,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
   auto afull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };
   auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };
+  auto eready_bar = [&](int g, int ii) { return bar0 + 8u * (2 * STAGES + 8 + g * 2 + ii); };
+  auto uready_bar = [&](int g, int ii) { return bar0 + 8u * (2 * STAGES + 12 + g * 2 + ii); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMEM_TMEMPTR);
 
   if (warp == 0 && lane == 0) {
@@ -224,6 +294,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS);
       mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS);
     }
+    for (int g = 0; g < 2; ++g)
+      for (int ii = 0; ii < 2; ++ii) { mbar_init(eready_bar(g, ii), 4); mbar_init(uready_bar(g, ii), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -240,6 +312,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   const long long first = DEBUG ? 0 : blockIdx.x;
   const long long step = DEBUG ? 1 : gridDim.x;
 
+  // Register budget: the control warpgroup (warps 0-3) gives registers back, the two epilogue
+  // warpgroups take them (128*64 + 256*216 <= 64K).
+  if (warp < EPI_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // =============================== TMA producer =========================================
     int stage = 0; uint32_t phase = 0;
@@ -252,8 +328,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       if (lane == 0) {
         const int n_valid = min(IMGS, p.n_img - n * IMGS);
         const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
-        mbar_expect_tx(afull_bar(b), n_valid * GRAM_FLOATS * 4 + AUX_META + AUX_WNORM);
-        bulk_load(aux, p.gram_tri + (size_t)n * IMGS * GRAM_FLOATS, n_valid * GRAM_FLOATS * 4, afull_bar(b));
+        mbar_expect_tx(afull_bar(b), n_valid * GRAM_BYTES + AUX_META + AUX_WNORM);
+        bulk_load(aux, p.gram_pack + (size_t)n * IMGS * GRAM_BYTES, n_valid * GRAM_BYTES, afull_bar(b));
         bulk_load(aux + AUX_GRAM, p.row_meta + (size_t)m * BLOCK_M, AUX_META, afull_bar(b));
         bulk_load(aux + AUX_GRAM + AUX_META, p.row_wnorm + (size_t)m * BLOCK_M, AUX_WNORM, afull_bar(b));
       }
@@ -270,7 +346,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===========================================
+    // =============================== main MMA issuer ======================================
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (long long t = first; t < total; t += step, ++it) {
@@ -295,13 +371,47 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else {
+    // =============================== Gram MMA issuers (warp 2 -> group 0, warp 3 -> group 1) =====
+    if (!DEBUG) {
+      const int g = warp - 2;
+      int it = 0;
+      uint32_t used[2] = {0u, 0u};     // completed phases of eready/uready[g][ii] (tail images are skipped)
+      for (long long t = first; t < total; t += step, ++it) {
+        int m, n;
+        sched.map(t, m, n);
+        const int b = it & 1;
+        mbar_wait(afull_bar(b), (it >> 1) & 1);
+        const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          const int img_in_tile = g * 2 + ii;
+          if (n * IMGS + img_in_tile >= p.n_img) continue;
+          mbar_wait(eready_bar(g, ii), used[ii]++ & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t te = tmem_base + b * ACC_COLS + e_col(img_in_tile);
+            const uint32_t tu = tmem_base + U_BASE + img_in_tile * GRAM_N;
+            const uint64_t gdesc = umma_desc_nosw(aux + img_in_tile * GRAM_BYTES, G_LBO, G_SBO);
+#pragma unroll
+            for (int k = 0; k < GRAM_N / UMMA_K; ++k)          // 16 fp16 = 8 TMEM columns, 2 core matrices
+              umma_f16_ts(tu, te + 8 * k, gdesc + (uint64_t)((2 * G_LBO * k) >> 4), IDESC_GRAM, k != 0);
+            umma_commit(uready_bar(g, ii));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  } else {
     // =============================== epilogue =============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
-    const int h = (warp - EPI_WARP0) >> 2;      // which pair of images of the tile
+    const int g = (warp - EPI_WARP0) >> 2;      // epilogue group = which pair of images of the tile
     const int row = q * 32 + lane;
     float* xch = reinterpret_cast<float*>(smem + SMEM_XCH);
     int it = 0;
+    uint32_t used0 = 0u, used1 = 0u;   // completed phases of uready[g][0/1] (tail images are skipped)
     for (long long t = first; t < total; t += step, ++it) {
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
@@ -319,22 +429,21 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 
       mbar_wait(tfull_bar(b), par);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + b * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+      const uint32_t tacc = tmem_base + b * ACC_COLS + lane_sel;
 
+      // per-image scalars carried from phase A to phase B
+      float Z0 = 0.f, P0 = 0.f, D0 = 0.f, Z1 = 0.f, P1 = 0.f, D1 = 0.f;
+
+      // ------------------------------- phase A, both images ---------------------------------
 #pragma unroll 1
       for (int ii = 0; ii < 2; ++ii) {
-        const int img_in_tile = h * 2 + ii;
+        const int img_in_tile = g * 2 + ii;
         const int img = n * IMGS + img_in_tile;
         float A[R];
         TMEM_LD_X32(tacc + img_in_tile * R, A, 0);
         TMEM_LD_X4(tacc + img_in_tile * R + 32, A, 32);
         tmem_ld_wait();
-        if (ii == 1) {
-          // both images of this warp are in registers: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(b));
-        }
         if (DEBUG) {
 #pragma unroll
           for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + img_in_tile * R + k] = A[k];
@@ -342,25 +451,27 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         }
         if (img >= p.n_img) continue;           // warp-uniform: zero-filled tail of the image set
 
-        // ---- l2norm denominators: sum over the caption's words of a^2, per region ----------
+        // l2norm denominators: sum over the caption's words of a^2, per region
         float E[R];
+        if (p.clipped) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-          float a = p.clipped ? fmaxf(A[k], 0.1f * A[k]) : A[k];
-          E[k] = a * a;
+          for (int k = 0; k < R; ++k) { float a = fmaxf(A[k], 0.1f * A[k]); E[k] = a * a; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < R; ++k) E[k] = A[k] * A[k];
         }
         if (!long_tile) {
 #pragma unroll
           for (int k = 0; k < R; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
         } else {
-          float* x = xch + ((h * 2 + ii) * 4) * 40;
+          float* x = xch + ((g * 2 + ii) * 4) * 40;
 #pragma unroll
           for (int k = 0; k < R; ++k) E[k] = warp_sum(E[k]);
           if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < R; k += 4) *reinterpret_cast<float4*>(x + q * 40 + k) = make_float4(E[k], E[k + 1], E[k + 2], E[k + 3]);
           }
-          named_bar_sync(1 + h, 128);
+          named_bar_sync(1 + g, 128);
 #pragma unroll
           for (int k = 0; k < R; k += 4) {
             float4 s0 = *reinterpret_cast<const float4*>(x + 0 * 40 + k), s1 = *reinterpret_cast<const float4*>(x + 1 * 40 + k);
@@ -369,64 +480,98 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
             E[k + 2] = (s0.z + s1.z) + (s2.z + s3.z); E[k + 3] = (s0.w + s1.w) + (s2.w + s3.w);
           }
         }
-        // ---- softmax numerators e_k = exp(lambda * ahat_k), Z, P -----------------------------
+        // softmax numerators, shifted by the largest possible exponent (|ahat| <= 1) so that e <= 1:
+        // no overflow in the fp16 copy for any lambda.  Z = sum e, P = sum e A, D = sum e^2.
         float smin = E[0];
 #pragma unroll
         for (int k = 1; k < R; ++k) smin = fminf(smin, E[k]);
-        float Z = 0.f, P = 0.f;
-        if (smin >= 1e-6f || cap < 0) {
-          // 1/(sqrt(S)+1e-8) = r (1 - 1e-8 r) + O((1e-8 r)^2),  r = rsqrt(S) <= 1e3
+        float Z = 0.f, P = 0.f, Dd = 0.f;
+        const float shift = -fabsf(p.c_sm);
+        if (smin >= 1e-4f || cap < 0) {
+          // 1/(sqrt(S)+1e-8) = rsqrt(S) (1 - O(1e-8 rsqrt(S))): relative difference <= 1e-6 for S >= 1e-4
 #pragma unroll
           for (int k = 0; k < R; ++k) {
             float a = p.clipped ? fmaxf(A[k], 0.1f * A[k]) : A[k];
-            float r = rsqf(E[k]);
-            float cr = p.c_sm * r;
-            float inv = fmaf(cr, -1e-8f * r, cr);
-            float e = ex2f(a * inv);
-            E[k] = e; Z += e; P = fmaf(e, A[k], P);
+            float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
+            E[k] = e; Z += e; P = fmaf(e, A[k], P); Dd = fmaf(e, e, Dd);
           }
         } else {
 #pragma unroll
           for (int k = 0; k < R; ++k) {
             float a = p.clipped ? fmaxf(A[k], 0.1f * A[k]) : A[k];
-            float inv = p.c_sm / (sqrtf(E[k]) + 1e-8f);
-            float e = ex2f(a * inv);
-            E[k] = e; Z += e; P = fmaf(e, A[k], P);
+            float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
+            E[k] = e; Z += e; P = fmaf(e, A[k], P); Dd = fmaf(e, e, Dd);
           }
         }
-        // ---- |ctx|^2 * Z^2 = e^T G e with the packed lower-triangular Gram (diagonal halved) ----
-        const float4* G = reinterpret_cast<const float4*>(aux + img_in_tile * GRAM_FLOATS * 4);
-        float Qh0 = 0.f, Qh1 = 0.f;
-        {
-          int off = 0;
+        if (ii == 0) { Z0 = Z; P0 = P; D0 = Dd; } else { Z1 = Z; P1 = P; D1 = Dd; }
+        // park e as fp16 over the image's dead accumulator columns (K padded 36 -> 48 with zeros)
+        uint32_t hv[24];
 #pragma unroll
-          for (int k = 0; k < R; ++k) {
-            float u0 = 0.f, u1 = 0.f;
+        for (int c = 0; c < 18; ++c) hv[c] = pack_f16x2(E[2 * c], E[2 * c + 1]);
 #pragma unroll
-            for (int g = 0; g <= k / 4; ++g) {
-              float4 gv = G[off + g];
-              u0 = fmaf(gv.x, E[4 * g + 0], u0); u1 = fmaf(gv.y, E[4 * g + 1], u1);
-              u0 = fmaf(gv.z, E[4 * g + 2], u0); u1 = fmaf(gv.w, E[4 * g + 3], u1);
-            }
-            off += k / 4 + 1;
-            if (k & 1) Qh1 = fmaf(E[k], u0 + u1, Qh1); else Qh0 = fmaf(E[k], u0 + u1, Qh0);
+        for (int c = 18; c < 24; ++c) hv[c] = 0u;
+        const uint32_t te = tacc + e_col(img_in_tile);
+        TMEM_ST_X16(te, hv, 0);
+        TMEM_ST_X8(te + 16, hv, 16);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(eready_bar(g, ii));
+      }
+
+      // ------------------------------- phase B, both images ---------------------------------
+#pragma unroll 1
+      for (int ii = 0; ii < 2; ++ii) {
+        const int img_in_tile = g * 2 + ii;
+        const int img = n * IMGS + img_in_tile;
+        const bool valid = !DEBUG && img < p.n_img;
+        float Qoff = 0.f;
+        if (valid) {
+          const uint32_t upar = (ii == 0 ? used0++ : used1++) & 1;
+          mbar_wait(uready_bar(g, ii), upar);
+          tc_fence_after();
+          float U[R];
+          uint32_t hv[24];
+          const uint32_t tu = tmem_base + U_BASE + img_in_tile * GRAM_N + lane_sel;
+          const uint32_t te = tacc + e_col(img_in_tile);
+          TMEM_LD_X32(tu, U, 0);
+          TMEM_LD_X4(tu + 32, U, 32);
+          TMEM_LD_X16U(te, hv, 0);
+          TMEM_LD_X8U(te + 16, hv, 16);
+          tmem_ld_wait();
+          // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form)
+          float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 18; ++c) {
+            float2 ef = unpack_f16x2(hv[c]);
+            q0 = fmaf(ef.x, U[2 * c], q0); q1 = fmaf(ef.y, U[2 * c + 1], q1);
           }
+          Qoff = q0 + q1;
         }
-        const float Qf = 2.f * (Qh0 + Qh1);
+        if (ii == 1) {
+          // last TMEM read of the accumulator buffer (raw affinities, parked e): hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(b));
+        }
+        if (!valid) continue;
+        const float Z = ii == 0 ? Z0 : Z1, P = ii == 0 ? P0 : P1, Dd = ii == 0 ? D0 : D1;
+        // e^T G e = sum e_k^2 (unit diagonal, fp32) + e^T (G - I) e (tensor core, fp16 operands)
+        const float Qf = Dd + Qoff;
         // r_j = (P/Z) / max(|w| sqrt(Q)/Z, 1e-8)
         const float rj = P / fmaxf(wnorm * sqrtf(fmaxf(Qf, 0.f)), 1e-8f * Z);
 
-        // ---- aggregate over the caption's words ------------------------------------------------
+        // aggregate over the caption's words
         float v = (p.agg == ITR_AGG_LSE) ? ex2f(rj * p.c_lse) : rj;
         if (cap < 0) v = (p.agg == ITR_AGG_MAX) ? -INFINITY : 0.f;
         float tot;
         if (!long_tile) {
           tot = (p.agg == ITR_AGG_MAX) ? seg_total<true>(v, pr, seg_hi) : seg_total<false>(v, pr, seg_hi);
         } else {
-          float* x = xch + ((h * 2 + ii) * 4) * 40 + 36;
+          float* x = xch + ((g * 2 + ii) * 4) * 40 + 36;
           tot = (p.agg == ITR_AGG_MAX) ? warp_max(v) : warp_sum(v);
           if (lane == 0) x[q * 40] = tot;
-          named_bar_sync(1 + h, 128);
+          named_bar_sync(1 + g, 128);
           float t0 = x[0], t1 = x[40], t2 = x[80], t3 = x[120];
           tot = (p.agg == ITR_AGG_MAX) ? fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) : (t0 + t1) + (t2 + t3);
         }
@@ -474,13 +619,15 @@ pack_words_kernel(const float* __restrict__ captions, int lmax, int d, const int
   if (lane == 0) wnorm[row] = sqrtf(ss);
 }
 
-// One block per image: round the 36 regions to bf16 and build the packed lower-triangular Gram.
+// One block per image: round the 36 regions to bf16 and build the image's Gram pack (fp16 off-diagonal
+// Gram in UMMA core-matrix order + fp32 diagonal) from the ROUNDED regions.
 __global__ void __launch_bounds__(256)
-prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out, float* __restrict__ gram_tri) {
+prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out, uint8_t* __restrict__ gram_pack) {
   extern __shared__ float sv[];   // [R][D+4] rounded values
   constexpr int LD = D + 4;
   const float* src = images + (size_t)blockIdx.x * R * D;
   uint16_t* dst = out + (size_t)blockIdx.x * R * D;
+  uint8_t* gp = gram_pack + (size_t)blockIdx.x * GRAM_BYTES;
   for (int e = threadIdx.x; e < R * D / 4; e += 256) {
     float4 x = reinterpret_cast<const float4*>(src)[e];
     uint16_t b0 = f32_to_bf16_rn(x.x), b1 = f32_to_bf16_rn(x.y), b2 = f32_to_bf16_rn(x.z), b3 = f32_to_bf16_rn(x.w);
@@ -488,25 +635,31 @@ prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out,
     int r = (e * 4) / D, c = (e * 4) % D;
     *reinterpret_cast<float4*>(&sv[r * LD + c]) = make_float4(bf16_to_f32(b0), bf16_to_f32(b1), bf16_to_f32(b2), bf16_to_f32(b3));
   }
+  // zero the padding rows / columns 36..47 of the fp16 block
+  for (int e = threadIdx.x; e < G16_BYTES / 4; e += 256) reinterpret_cast<uint32_t*>(gp)[e] = 0u;
   __syncthreads();
-  // 720 packed outputs: row k holds k2 = 0 .. 4*(k/4)+3, zero beyond k, diagonal halved
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* g = gram_tri + (size_t)blockIdx.x * GRAM_FLOATS;
-  for (int o = warp; o < GRAM_FLOATS; o += 8) {
-    // locate (k, k2) of packed offset o: rows come in groups of four with equal length 4*(grp+1)
-    int grp = 0, base = 0;
-    while (o >= base + 16 * (grp + 1)) { base += 16 * (grp + 1); ++grp; }
-    int len = 4 * (grp + 1);
-    int k = 4 * grp + (o - base) / len, k2 = (o - base) % len;
+  __half* g16 = reinterpret_cast<__half*>(gp);
+  float* gd = reinterpret_cast<float*>(gp + G16_BYTES);
+  for (int o = warp; o < R * (R + 1) / 2; o += 8) {
+    int k = 0, rem = o;
+    while (rem > k) { rem -= k + 1; ++k; }     // o -> (k, k2 = rem), k2 <= k
+    const int k2 = rem;
+    const float* a = sv + k * LD;
+    const float* bq = sv + k2 * LD;
     float s = 0.f;
-    if (k2 <= k) {
-      const float* a = sv + k * LD;
-      const float* bq = sv + k2 * LD;
-      for (int c = lane; c < D; c += 32) s = fmaf(a[c], bq[c], s);
-      s = warp_sum(s);
-      if (k2 == k) s *= 0.5f;
+    for (int c = lane; c < D; c += 32) s = fmaf(a[c], bq[c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (k == k2) {
+        gd[k] = s;
+        g16[(k / 8) * (G_SBO / 2) + (k / 8) * (G_LBO / 2) + (k % 8) * 8 + (k % 8)] = __float2half_rn(s - 1.0f);
+      } else {
+        const __half hs = __float2half_rn(s);
+        g16[(k / 8) * (G_SBO / 2) + (k2 / 8) * (G_LBO / 2) + (k % 8) * 8 + (k2 % 8)] = hs;
+        g16[(k2 / 8) * (G_SBO / 2) + (k / 8) * (G_LBO / 2) + (k2 % 8) * 8 + (k % 8)] = hs;
+      }
     }
-    if (lane == 0) g[o] = s;
   }
 }
 
@@ -573,18 +726,18 @@ extern "C" int itr_scan_pack_words_bf16(const float* captions, int n_cap, int lm
 }
 
 extern "C" int itr_scan_prep_images_bf16(const float* images, int n_img, int n_regions, int d, uint16_t* images_bf16,
-                                         float* gram_tri, void* stream) {
-  ITR_REQUIRE(images && images_bf16 && gram_tri, "itr_scan_prep_images_bf16: null pointer");
+                                         void* gram_pack, void* stream) {
+  ITR_REQUIRE(images && images_bf16 && gram_pack, "itr_scan_prep_images_bf16: null pointer");
   ITR_REQUIRE(n_regions == R && d == D, "itr_scan_prep_images_bf16: built for %d regions x %d dims, got %d x %d", R, D, n_regions, d);
   if (n_img <= 0) return ITR_OK;
   const int smem = R * (D + 4) * 4;
   ITR_CHECK_CUDA(cudaFuncSetAttribute(prep_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  prep_images_kernel<<<n_img, 256, smem, as_stream(stream)>>>(images, images_bf16, gram_tri);
+  prep_images_kernel<<<n_img, 256, smem, as_stream(stream)>>>(images, images_bf16, reinterpret_cast<uint8_t*>(gram_pack));
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }
 
-static int launch_tc(const uint16_t* images_bf16, const float* gram_tri, int n_img, const uint16_t* words_bf16,
+static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
                      const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
                      float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, float* dump, int dbg_m,
                      int dbg_n, void* stream) {
@@ -596,7 +749,7 @@ static int launch_tc(const uint16_t* images_bf16, const float* gram_tri, int n_i
   rc = make_map(&map_i, images_bf16, (uint64_t)n_img * R, BLOCK_N);
   if (rc) return rc;
   Params p{};
-  p.gram_tri = gram_tri;
+  p.gram_pack = reinterpret_cast<const uint8_t*>(gram_pack);
   p.row_meta = reinterpret_cast<const int4*>(row_meta);
   p.row_wnorm = row_wnorm;
   p.n_img = n_img; p.n_wt = n_tiles; p.n_it = (n_img + IMGS - 1) / IMGS;
@@ -621,20 +774,20 @@ static int launch_tc(const uint16_t* images_bf16, const float* gram_tri, int n_i
   return ITR_OK;
 }
 
-extern "C" int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const float* gram_tri, int n_img,
+extern "C" int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const void* gram_pack, int n_img,
                                         const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                                         int n_tiles, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                                         float* scores, int64_t ld_scores, void* stream) {
-  ITR_REQUIRE(images_bf16 && gram_tri && words_bf16 && row_meta && row_wnorm && scores, "itr_scan_t2i_scores_bf16: null pointer");
+  ITR_REQUIRE(images_bf16 && gram_pack && words_bf16 && row_meta && row_wnorm && scores, "itr_scan_t2i_scores_bf16: null pointer");
   ITR_REQUIRE(feature_norm == ITR_NORM_CLIPPED_L2 || feature_norm == ITR_NORM_L2,
               "itr_scan_t2i_scores_bf16: raw_feature_norm %d is only available in the float32 path", feature_norm);
   ITR_REQUIRE(agg >= 0 && agg <= ITR_AGG_SUM, "unknown aggfunc: %d", agg);
   ITR_REQUIRE(lambda_lse != 0.f || agg != ITR_AGG_LSE, "itr_scan_t2i_scores_bf16: lambda_lse must be non-zero");
   ITR_REQUIRE(lambda_softmax > -80.f && lambda_softmax < 80.f, "itr_scan_t2i_scores_bf16: |lambda_softmax| must be < 80");
-  ITR_REQUIRE(((uintptr_t)images_bf16 & 15) == 0 && ((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)gram_tri & 15) == 0 &&
+  ITR_REQUIRE(((uintptr_t)images_bf16 & 15) == 0 && ((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)gram_pack & 15) == 0 &&
               ((uintptr_t)row_meta & 15) == 0 && ((uintptr_t)row_wnorm & 15) == 0, "itr_scan_t2i_scores_bf16: buffers must be 16-byte aligned");
   if (n_img <= 0 || n_tiles <= 0) return ITR_OK;
-  return launch_tc(images_bf16, gram_tri, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
+  return launch_tc(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
                    lambda_softmax, lambda_lse, scores, ld_scores, nullptr, 0, 0, stream);
 }
 
@@ -644,7 +797,7 @@ extern "C" int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_im
   ITR_REQUIRE(word_tile >= 0 && word_tile < n_tiles && image_tile >= 0 && image_tile * IMGS < n_img,
               "itr_scan_t2i_affinity_debug: tile index out of range");
   // aux loads still run; point them at the operand buffers (contents unused in debug mode)
-  return launch_tc(images_bf16, reinterpret_cast<const float*>(images_bf16), n_img, words_bf16,
+  return launch_tc(images_bf16, images_bf16, n_img, words_bf16,
                    reinterpret_cast<const int32_t*>(words_bf16), reinterpret_cast<const float*>(words_bf16), n_tiles,
                    ITR_NORM_CLIPPED_L2, ITR_AGG_SUM, 1.f, 1.f, out, 0, out, word_tile, image_tile, stream);
 }

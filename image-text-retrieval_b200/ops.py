@@ -78,7 +78,7 @@ def scan_scores_f32(images, captions, cap_lens, cross_attn, raw_feature_norm, ag
 @dataclass
 class PreparedImages:
     images_bf16: torch.Tensor     # (n_img, 36, 1024) bf16
-    gram_tri: torch.Tensor        # (n_img, 720) f32
+    gram_pack: torch.Tensor       # (n_img, 4752) u8: fp16 off-diagonal Gram (UMMA layout) + fp32 diagonal
     n_img: int
 
 
@@ -117,7 +117,7 @@ def prepare_images(images) -> PreparedImages:
     images = _cuda_f32(images, "images")
     n_img = images.size(0)
     out = torch.empty(n_img, capi.REGIONS, capi.EMBED, device=images.device, dtype=torch.bfloat16)
-    gram = torch.empty(n_img, capi.GRAM_TRI, device=images.device, dtype=torch.float32)
+    gram = torch.empty(n_img, capi.GRAM_BYTES, device=images.device, dtype=torch.uint8)
     with torch.cuda.device(images.device):
         check(capi.lib().itr_scan_prep_images_bf16(ptr(images), n_img, images.size(1), images.size(2), ptr(out), ptr(gram),
                                                    stream_ptr()))
@@ -159,7 +159,7 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
         out = torch.empty(pi.n_img, pc.n_cap, device=dev, dtype=torch.float32)
     assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
     with torch.cuda.device(dev):
-        check(capi.lib().itr_scan_t2i_scores_bf16(ptr(pi.images_bf16), ptr(pi.gram_tri), pi.n_img, ptr(pc.words_bf16),
+        check(capi.lib().itr_scan_t2i_scores_bf16(ptr(pi.images_bf16), ptr(pi.gram_pack), pi.n_img, ptr(pc.words_bf16),
                                                   ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, norm, agg,
                                                   float(lambda_softmax), float(lambda_lse), ptr(out),
                                                   out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))

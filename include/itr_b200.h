@@ -50,7 +50,7 @@ extern "C" {
 #define ITR_EMBED          1024  /* embed_size, itr/config.py:73 */
 #define ITR_TILE_WORDS     128   /* rows of one packed word tile (= UMMA M) */
 #define ITR_TILE_IMAGES    4     /* images per accumulator tile (UMMA N = 4*36 = 144) */
-#define ITR_GRAM_TRI       720   /* floats per image of the packed lower-triangular region Gram */
+#define ITR_GRAM_BYTES     4752  /* bytes per image of the Gram pack: fp16 48x48 off-diagonal Gram in UMMA core-matrix order + 36 fp32 diagonal entries */
 #define ITR_MAX_WORDS_F32  80    /* longest caption the fp32 validation kernel accepts */
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -87,8 +87,9 @@ int itr_scan_scores_f32(const float* images, const float* gram, const float* cap
  * 2. itr_scan_pack_words_bf16: gathers the words (captions may live in device memory or in
  *    pinned host memory mapped into the device address space), rounds to bf16 and writes each
  *    row's L2 norm (of the rounded values).
- * 3. itr_scan_prep_images_bf16: rounds regions to bf16 and writes the packed lower-triangular
- *    36x36 Gram matrix of the rounded regions (diagonal pre-halved), ITR_GRAM_TRI floats per image.
+ * 3. itr_scan_prep_images_bf16: rounds regions to bf16 and writes, per image, the Gram pack of the
+ *    rounded regions (ITR_GRAM_BYTES): G = V V^T with the off-diagonal part in fp16, laid out as the
+ *    SMEM B operand of a 128x48x48 tcgen05.mma, and the diagonal in fp32.
  * 4. itr_scan_t2i_scores_bf16: persistent TMA -> tcgen05.mma -> TMEM epilogue kernel.
  */
 int itr_scan_plan_max_tiles(const int32_t* cap_lens_host, int n_cap);
@@ -97,8 +98,8 @@ int itr_scan_pack_words_bf16(const float* captions, int n_cap, int lmax, int d,
                              const int32_t* row_meta, int n_tiles,
                              uint16_t* words_bf16, float* row_wnorm, void* stream);
 int itr_scan_prep_images_bf16(const float* images, int n_img, int n_regions, int d,
-                              uint16_t* images_bf16, float* gram_tri, void* stream);
-int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const float* gram_tri, int n_img,
+                              uint16_t* images_bf16, void* gram_pack, void* stream);
+int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const void* gram_pack, int n_img,
                              const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                              int n_tiles, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                              float* scores, int64_t ld_scores, void* stream);

@@ -55,16 +55,21 @@ def test_affinity_tile_matches_matmul():
             v[: len(rows)] = rows
             want = words[wt].astype(np.float64) @ v.T
             np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
-    # packed lower-triangular Gram (diagonal halved) of the rounded regions
+    # Gram pack of the rounded regions: fp16 off-diagonal block in UMMA core-matrix order + fp32 diagonal
     G = np.einsum("ikd,ild->ikl", img.numpy().astype(np.float64), img.numpy().astype(np.float64))
-    tri = pi.gram_tri.cpu().numpy()
-    off = 0
-    for k in range(36):
-        ln = 4 * (k // 4 + 1)
-        want = np.zeros(ln); want[: k + 1] = G[0, k, : k + 1]; want[k] *= 0.5
-        np.testing.assert_allclose(tri[0, off: off + ln], want, rtol=1e-5, atol=1e-6)
-        off += ln
-    assert off == 720
+    pack = pi.gram_pack.cpu().numpy()
+    assert pack.shape == (11, 4752)
+    for i in (0, 10):
+        g16 = pack[i, :4608].copy().view(np.float16).astype(np.float64)
+        gd = pack[i, 4608:].copy().view(np.float32)
+        np.testing.assert_allclose(gd, np.diag(G[i]), rtol=1e-6)
+        dense = np.zeros((48, 48))
+        for n_ in range(48):
+            for k_ in range(48):
+                dense[n_, k_] = g16[(n_ // 8) * 384 + (k_ // 8) * 64 + (n_ % 8) * 8 + (k_ % 8)]
+        want = G[i] - np.eye(36)          # unit diagonal stays in fp32 on the CUDA cores (sum_k e_k^2)
+        np.testing.assert_allclose(dense[:36, :36], want, rtol=1e-3, atol=1e-6)      # fp16 rounding
+        assert (dense[36:] == 0).all() and (dense[:, 36:] == 0).all()
 
 
 @pytest.mark.parametrize("case", ["scan_small", "scan_long"])
