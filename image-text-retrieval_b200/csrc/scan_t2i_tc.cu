@@ -70,14 +70,14 @@ constexpr int AUX_GRAM = IMGS * GRAM_BYTES;        // 19008
 constexpr int AUX_META = BLOCK_M * 16;             // 2048
 constexpr int AUX_WNORM = BLOCK_M * 4;             // 512
 constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 21568
-constexpr int XCH_FLOATS = 2 /*group*/ * 2 /*image*/ * 4 /*warp*/ * 40;
+constexpr int XCH_FLOATS = 4 /*group*/ * 4 /*warp*/ * 40;
 constexpr int ACC_COLS = 144;                  // column stride between the two accumulators
 constexpr int U_BASE = 288;                    // four 48-column Gram-product buffers: [288, 480)
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 32;                       // word tiles kept L2-resident while images stream
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 640;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 
 constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
@@ -199,6 +199,16 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
                : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]),    \
                  "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])                                     \
                : "r"(taddr))
+#define TMEM_LD_X2U(taddr, v, o) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[o + 0]), "=r"(v[o + 1]) : "r"(taddr))
+#define TMEM_LD_X1F(taddr, f) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(f) : "r"(taddr))
+#define TMEM_ST_X4(taddr, v, o) \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]) : "memory")
+#define TMEM_ST_X2(taddr, v, o) \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]) : "memory")
+#define TMEM_ST_X1(taddr, r0) \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r0) : "memory")
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
@@ -221,15 +231,15 @@ struct Schedule {
     last_band = n_wt - full_bands * BAND;
     full_items = full_bands * BAND * n_it;
   }
-  __device__ long long total() const { return (long long)n_wt * n_it; }
-  __device__ void map(long long t, int& m, int& n) const {
+  __device__ int total() const { return n_wt * n_it; }      // host guarantees < 2^31
+  __device__ void map(int t, int& m, int& n) const {
     if (t < full_items) {
-      int band = (int)(t / ((long long)BAND * n_it));
-      int local = (int)(t - (long long)band * BAND * n_it);
+      int band = t / (BAND * n_it);
+      int local = t - band * BAND * n_it;
       n = local / BAND;
       m = band * BAND + local % BAND;
     } else {
-      int local = (int)(t - full_items);
+      int local = t - full_items;
       n = local / last_band;
       m = (n_wt - last_band) + local % last_band;
     }
@@ -265,6 +275,13 @@ __device__ __forceinline__ float seg_total(float x, const bool (&p)[5], int seg_
 // 16-column aligned and inside the image's own 36 columns [36 i, 36 i + 36)
 __device__ __forceinline__ int e_col(int i) { return i == 0 ? 0 : 16 + 32 * i; }   // 0, 48, 80, 112
 
+// what phase B of an item needs from its phase A (phase B runs one item later, see below)
+struct Carry {
+  float P, D, wnorm;
+  int cap, seg, n_words, img, b;
+  bool valid, live;
+};
+
 template <bool DEBUG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
@@ -280,8 +297,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
   auto afull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };
   auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };
-  auto eready_bar = [&](int g, int ii) { return bar0 + 8u * (2 * STAGES + 8 + g * 2 + ii); };
-  auto uready_bar = [&](int g, int ii) { return bar0 + 8u * (2 * STAGES + 12 + g * 2 + ii); };
+  auto eready_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 8 + g); };
+  auto uready_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 12 + g); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMEM_TMEMPTR);
 
   if (warp == 0 && lane == 0) {
@@ -294,8 +311,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS);
       mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS);
     }
-    for (int g = 0; g < 2; ++g)
-      for (int ii = 0; ii < 2; ++ii) { mbar_init(eready_bar(g, ii), 4); mbar_init(uready_bar(g, ii), 1); }
+    for (int g = 0; g < IMGS; ++g) { mbar_init(eready_bar(g), 4); mbar_init(uready_bar(g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -308,31 +324,20 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const Schedule sched(p.n_wt, p.n_it);
-  const long long total = DEBUG ? 1 : sched.total();
-  const long long first = DEBUG ? 0 : blockIdx.x;
-  const long long step = DEBUG ? 1 : gridDim.x;
+  const int total = DEBUG ? 1 : sched.total();
+  const int first = DEBUG ? 0 : (int)blockIdx.x;
+  const int step = DEBUG ? 1 : (int)gridDim.x;
 
-  // Register budget: the control warpgroup (warps 0-3) gives registers back, the two epilogue
-  // warpgroups take them (128*64 + 256*216 <= 64K).
+  // Register budget: the control warpgroup (warps 0-3) gives registers back, the four epilogue
+  // warpgroups take them (128*40 + 512*104 <= 64K).
   if (warp < EPI_WARP0) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
-    // =============================== TMA producer =========================================
+    // =============================== TMA producer: operand ring ============================
     int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (long long t = first; t < total; t += step, ++it) {
+    for (int t = first; t < total; t += step) {
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
-      const int b = it & 1;
-      mbar_wait(aempty_bar(b), ((it >> 1) & 1) ^ 1);
-      if (lane == 0) {
-        const int n_valid = min(IMGS, p.n_img - n * IMGS);
-        const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
-        mbar_expect_tx(afull_bar(b), n_valid * GRAM_BYTES + AUX_META + AUX_WNORM);
-        bulk_load(aux, p.gram_pack + (size_t)n * IMGS * GRAM_BYTES, n_valid * GRAM_BYTES, afull_bar(b));
-        bulk_load(aux + AUX_GRAM, p.row_meta + (size_t)m * BLOCK_M, AUX_META, afull_bar(b));
-        bulk_load(aux + AUX_GRAM + AUX_META, p.row_wnorm + (size_t)m * BLOCK_M, AUX_WNORM, afull_bar(b));
-      }
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (lane == 0) {
@@ -349,7 +354,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     // =============================== main MMA issuer ======================================
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (long long t = first; t < total; t += step, ++it) {
+    for (int t = first; t < total; t += step, ++it) {
       const int b = it & 1;
       mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -371,204 +376,108 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
-    // =============================== Gram MMA issuers (warp 2 -> group 0, warp 3 -> group 1) =====
+  } else if (warp == 2) {
+    // =============================== Gram MMA issuer =======================================
+    // U_g = e_g (G_g - I): A = the group's parked fp16 numerators (TMEM), B = the image's Gram pack (SMEM)
     if (!DEBUG) {
-      const int g = warp - 2;
       int it = 0;
-      uint32_t used[2] = {0u, 0u};     // completed phases of eready/uready[g][ii] (tail images are skipped)
-      for (long long t = first; t < total; t += step, ++it) {
+      uint32_t used[IMGS] = {0u, 0u, 0u, 0u};    // completed phases of eready[g] (tail images are skipped)
+      for (int t = first; t < total; t += step, ++it) {
         int m, n;
         sched.map(t, m, n);
         const int b = it & 1;
         mbar_wait(afull_bar(b), (it >> 1) & 1);
         const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
 #pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          const int img_in_tile = g * 2 + ii;
-          if (n * IMGS + img_in_tile >= p.n_img) continue;
-          mbar_wait(eready_bar(g, ii), used[ii]++ & 1);
+        for (int g = 0; g < IMGS; ++g) {
+          if (n * IMGS + g >= p.n_img) continue;
+          mbar_wait(eready_bar(g), used[g]++ & 1);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t te = tmem_base + b * ACC_COLS + e_col(img_in_tile);
-            const uint32_t tu = tmem_base + U_BASE + img_in_tile * GRAM_N;
-            const uint64_t gdesc = umma_desc_nosw(aux + img_in_tile * GRAM_BYTES, G_LBO, G_SBO);
+            const uint32_t te = tmem_base + b * ACC_COLS + e_col(g);
+            const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
+            const uint64_t gdesc = umma_desc_nosw(aux + g * GRAM_BYTES, G_LBO, G_SBO);
 #pragma unroll
             for (int k = 0; k < GRAM_N / UMMA_K; ++k)          // 16 fp16 = 8 TMEM columns, 2 core matrices
               umma_f16_ts(tu, te + 8 * k, gdesc + (uint64_t)((2 * G_LBO * k) >> 4), IDESC_GRAM, k != 0);
-            umma_commit(uready_bar(g, ii));
+            umma_commit(uready_bar(g));
           }
           __syncwarp();
         }
       }
     }
-  }
   } else {
-    // =============================== epilogue =============================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int q = warp & 3;                     // TMEM lane quarter this warp may access
-    const int g = (warp - EPI_WARP0) >> 2;      // epilogue group = which pair of images of the tile
-    const int row = q * 32 + lane;
-    float* xch = reinterpret_cast<float*>(smem + SMEM_XCH);
+    // =============================== aux loader: Gram packs, row metadata, word norms ======
     int it = 0;
-    uint32_t used0 = 0u, used1 = 0u;   // completed phases of uready[g][0/1] (tail images are skipped)
-    for (long long t = first; t < total; t += step, ++it) {
+    for (int t = first; t < total; t += step, ++it) {
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
       const int b = it & 1;
-      const uint32_t par = (it >> 1) & 1;
-      mbar_wait(afull_bar(b), par);
-      const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
-      const int4 meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
-      const float wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
-      const int cap = meta.x, seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff, n_words = meta.w;
-      const bool long_tile = (meta.z >> 16) & 1;
-      bool pr[5];
-#pragma unroll
-      for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
-
-      mbar_wait(tfull_bar(b), par);
-      tc_fence_after();
-      const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-      const uint32_t tacc = tmem_base + b * ACC_COLS + lane_sel;
-
-      // per-image scalars carried from phase A to phase B
-      float Z0 = 0.f, P0 = 0.f, D0 = 0.f, Z1 = 0.f, P1 = 0.f, D1 = 0.f;
-
-      // ------------------------------- phase A, both images ---------------------------------
-#pragma unroll 1
-      for (int ii = 0; ii < 2; ++ii) {
-        const int img_in_tile = g * 2 + ii;
-        const int img = n * IMGS + img_in_tile;
-        float A[R];
-        TMEM_LD_X32(tacc + img_in_tile * R, A, 0);
-        TMEM_LD_X4(tacc + img_in_tile * R + 32, A, 32);
-        tmem_ld_wait();
-        if (DEBUG) {
-#pragma unroll
-          for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + img_in_tile * R + k] = A[k];
-          continue;
-        }
-        if (img >= p.n_img) continue;           // warp-uniform: zero-filled tail of the image set
-
-        // l2norm denominators: sum over the caption's words of a^2, per region
-        float E[R];
-        if (p.clipped) {
-#pragma unroll
-          for (int k = 0; k < R; ++k) { float a = fmaxf(A[k], 0.1f * A[k]); E[k] = a * a; }
-        } else {
-#pragma unroll
-          for (int k = 0; k < R; ++k) E[k] = A[k] * A[k];
-        }
-        if (!long_tile) {
-#pragma unroll
-          for (int k = 0; k < R; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
-        } else {
-          float* x = xch + ((g * 2 + ii) * 4) * 40;
-#pragma unroll
-          for (int k = 0; k < R; ++k) E[k] = warp_sum(E[k]);
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < R; k += 4) *reinterpret_cast<float4*>(x + q * 40 + k) = make_float4(E[k], E[k + 1], E[k + 2], E[k + 3]);
-          }
-          named_bar_sync(1 + g, 128);
-#pragma unroll
-          for (int k = 0; k < R; k += 4) {
-            float4 s0 = *reinterpret_cast<const float4*>(x + 0 * 40 + k), s1 = *reinterpret_cast<const float4*>(x + 1 * 40 + k);
-            float4 s2 = *reinterpret_cast<const float4*>(x + 2 * 40 + k), s3 = *reinterpret_cast<const float4*>(x + 3 * 40 + k);
-            E[k] = (s0.x + s1.x) + (s2.x + s3.x); E[k + 1] = (s0.y + s1.y) + (s2.y + s3.y);
-            E[k + 2] = (s0.z + s1.z) + (s2.z + s3.z); E[k + 3] = (s0.w + s1.w) + (s2.w + s3.w);
-          }
-        }
-        // softmax numerators, shifted by the largest possible exponent (|ahat| <= 1) so that e <= 1:
-        // no overflow in the fp16 copy for any lambda.  Z = sum e, P = sum e A, D = sum e^2.
-        float smin = E[0];
-#pragma unroll
-        for (int k = 1; k < R; ++k) smin = fminf(smin, E[k]);
-        float Z = 0.f, P = 0.f, Dd = 0.f;
-        const float shift = -fabsf(p.c_sm);
-        if (smin >= 1e-4f || cap < 0) {
-          // 1/(sqrt(S)+1e-8) = rsqrt(S) (1 - O(1e-8 rsqrt(S))): relative difference <= 1e-6 for S >= 1e-4
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            float a = p.clipped ? fmaxf(A[k], 0.1f * A[k]) : A[k];
-            float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
-            E[k] = e; Z += e; P = fmaf(e, A[k], P); Dd = fmaf(e, e, Dd);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            float a = p.clipped ? fmaxf(A[k], 0.1f * A[k]) : A[k];
-            float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
-            E[k] = e; Z += e; P = fmaf(e, A[k], P); Dd = fmaf(e, e, Dd);
-          }
-        }
-        if (ii == 0) { Z0 = Z; P0 = P; D0 = Dd; } else { Z1 = Z; P1 = P; D1 = Dd; }
-        // park e as fp16 over the image's dead accumulator columns (K padded 36 -> 48 with zeros)
-        uint32_t hv[24];
-#pragma unroll
-        for (int c = 0; c < 18; ++c) hv[c] = pack_f16x2(E[2 * c], E[2 * c + 1]);
-#pragma unroll
-        for (int c = 18; c < 24; ++c) hv[c] = 0u;
-        const uint32_t te = tacc + e_col(img_in_tile);
-        TMEM_ST_X16(te, hv, 0);
-        TMEM_ST_X8(te + 16, hv, 16);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(eready_bar(g, ii));
+      mbar_wait(aempty_bar(b), ((it >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        const int n_valid = min(IMGS, p.n_img - n * IMGS);
+        const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
+        mbar_expect_tx(afull_bar(b), n_valid * GRAM_BYTES + AUX_META + AUX_WNORM);
+        bulk_load(aux, p.gram_pack + (size_t)n * IMGS * GRAM_BYTES, n_valid * GRAM_BYTES, afull_bar(b));
+        bulk_load(aux + AUX_GRAM, p.row_meta + (size_t)m * BLOCK_M, AUX_META, afull_bar(b));
+        bulk_load(aux + AUX_GRAM + AUX_META, p.row_wnorm + (size_t)m * BLOCK_M, AUX_WNORM, afull_bar(b));
       }
+      __syncwarp();
+    }
+  }
+  } else {
+    // =============================== epilogue =============================================
+    // Group g (4 warps = all 128 word rows) owns image g of every tile.  Per item: phase B of the
+    // PREVIOUS item first (its Gram product has long landed), then phase A of the current one.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int g = (warp - EPI_WARP0) >> 2;      // epilogue group = image of the tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
+    uint32_t used = 0u;                         // completed phases of uready[g]
+    Carry c;
+    c.live = false; c.valid = false; c.P = c.D = c.wnorm = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
 
-      // ------------------------------- phase B, both images ---------------------------------
-#pragma unroll 1
-      for (int ii = 0; ii < 2; ++ii) {
-        const int img_in_tile = g * 2 + ii;
-        const int img = n * IMGS + img_in_tile;
-        const bool valid = !DEBUG && img < p.n_img;
-        float Qoff = 0.f;
-        if (valid) {
-          const uint32_t upar = (ii == 0 ? used0++ : used1++) & 1;
-          mbar_wait(uready_bar(g, ii), upar);
-          tc_fence_after();
-          float U[R];
-          uint32_t hv[24];
-          const uint32_t tu = tmem_base + U_BASE + img_in_tile * GRAM_N + lane_sel;
-          const uint32_t te = tacc + e_col(img_in_tile);
-          TMEM_LD_X32(tu, U, 0);
-          TMEM_LD_X4(tu + 32, U, 32);
-          TMEM_LD_X16U(te, hv, 0);
-          TMEM_LD_X8U(te + 16, hv, 16);
-          tmem_ld_wait();
-          // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form)
-          float q0 = 0.f, q1 = 0.f;
+    auto phase_b = [&]() {
+      // ---------------- phase B of the carried item: cosine + aggregation + store -------------
+      if (c.valid) {
+        const int seg_lo = c.seg & 0xff, seg_hi = (c.seg >> 8) & 0xff;
+        const bool long_tile = (c.seg >> 16) & 1;
+        mbar_wait(uready_bar(g), used++ & 1);
+        tc_fence_after();
+        float U[R];
+        uint32_t hv[18];
+        const uint32_t tu = tmem_base + U_BASE + g * GRAM_N + lane_sel;
+        const uint32_t te = tmem_base + c.b * ACC_COLS + lane_sel + e_col(g);
+        TMEM_LD_X32(tu, U, 0);
+        TMEM_LD_X4(tu + 32, U, 32);
+        TMEM_LD_X16U(te, hv, 0);
+        TMEM_LD_X2U(te + 16, hv, 16);
+        float Zsum;
+        TMEM_LD_X1F(tu + 36, Zsum);              // ones column of the Gram pack: sum_k e_k
+        tmem_ld_wait();
+        // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form)
+        float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-          for (int c = 0; c < 18; ++c) {
-            float2 ef = unpack_f16x2(hv[c]);
-            q0 = fmaf(ef.x, U[2 * c], q0); q1 = fmaf(ef.y, U[2 * c + 1], q1);
-          }
-          Qoff = q0 + q1;
+        for (int cidx = 0; cidx < 18; ++cidx) {
+          float2 ef = unpack_f16x2(hv[cidx]);
+          q0 = fmaf(ef.x, U[2 * cidx], q0); q1 = fmaf(ef.y, U[2 * cidx + 1], q1);
         }
-        if (ii == 1) {
-          // last TMEM read of the accumulator buffer (raw affinities, parked e): hand it back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(b));
-        }
-        if (!valid) continue;
-        const float Z = ii == 0 ? Z0 : Z1, P = ii == 0 ? P0 : P1, Dd = ii == 0 ? D0 : D1;
         // e^T G e = sum e_k^2 (unit diagonal, fp32) + e^T (G - I) e (tensor core, fp16 operands)
-        const float Qf = Dd + Qoff;
+        const float Qf = c.D + (q0 + q1);
         // r_j = (P/Z) / max(|w| sqrt(Q)/Z, 1e-8)
-        const float rj = P / fmaxf(wnorm * sqrtf(fmaxf(Qf, 0.f)), 1e-8f * Z);
-
-        // aggregate over the caption's words
+        const float rj = c.P / fmaxf(c.wnorm * sqrtf(fmaxf(Qf, 0.f)), 1e-8f * Zsum);
+        bool pr[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
         float v = (p.agg == ITR_AGG_LSE) ? ex2f(rj * p.c_lse) : rj;
-        if (cap < 0) v = (p.agg == ITR_AGG_MAX) ? -INFINITY : 0.f;
+        if (c.cap < 0) v = (p.agg == ITR_AGG_MAX) ? -INFINITY : 0.f;
         float tot;
         if (!long_tile) {
           tot = (p.agg == ITR_AGG_MAX) ? seg_total<true>(v, pr, seg_hi) : seg_total<false>(v, pr, seg_hi);
         } else {
-          float* x = xch + ((g * 2 + ii) * 4) * 40 + 36;
+          float* x = xch + 36;
           tot = (p.agg == ITR_AGG_MAX) ? warp_max(v) : warp_sum(v);
           if (lane == 0) x[q * 40] = tot;
           named_bar_sync(1 + g, 128);
@@ -576,13 +485,123 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
           tot = (p.agg == ITR_AGG_MAX) ? fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) : (t0 + t1) + (t2 + t3);
         }
         if (p.agg == ITR_AGG_LSE) tot = lg2f(tot) * p.inv_lse;
-        if (p.agg == ITR_AGG_MEAN) tot = tot / (float)n_words;
+        if (p.agg == ITR_AGG_MEAN) tot = tot / (float)c.n_words;
         const bool writer = long_tile ? (row == 0) : (lane == seg_lo);
-        if (writer && cap >= 0) p.scores[(size_t)img * p.ld + cap] = tot;
+        if (writer && c.cap >= 0) p.scores[(size_t)c.img * p.ld + c.cap] = tot;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(aempty_bar(b));
+      if (c.live) {
+        // every TMEM / SMEM read of that item is complete: hand its accumulator and aux buffers back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(tempty_bar(c.b)); mbar_arrive(aempty_bar(c.b)); }
+      }
+    };
+
+    int it = 0;
+    for (int t = first; t < total; t += step, ++it) {
+      phase_b();
+
+      int m, n;
+      if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
+      const int b = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      mbar_wait(afull_bar(b), par);
+      const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
+      const int4 meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
+      c.wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
+      c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w; c.b = b; c.live = true;
+      c.img = n * IMGS + g;
+      c.valid = !DEBUG && c.img < p.n_img;
+      const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
+      const bool long_tile = (meta.z >> 16) & 1;
+
+      mbar_wait(tfull_bar(b), par);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + b * ACC_COLS + lane_sel;
+      if (DEBUG || c.valid) {
+        // ---------------- phase A: raw affinities -> softmax numerators, parked as fp16 ---------
+        float A[R];
+        TMEM_LD_X32(tacc + g * R, A, 0);
+        TMEM_LD_X4(tacc + g * R + 32, A, 32);
+        tmem_ld_wait();
+        if (DEBUG) {
+#pragma unroll
+          for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + g * R + k] = A[k];
+        } else {
+          bool pr[5];
+#pragma unroll
+          for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
+          float P = 0.f, Dd = 0.f;
+          const float shift = -fabsf(p.c_sm);
+          const uint32_t te = tacc + e_col(g);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {          // two halves of 18 regions: bounds the live registers
+            float E[R / 2];
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) {
+              float a = p.clipped ? fmaxf(A[18 * h + k], 0.1f * A[18 * h + k]) : A[18 * h + k];
+              E[k] = a * a;
+            }
+            // l2norm denominators: sum over the caption's words of a^2, per region
+            if (!long_tile) {
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
+            } else {
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) E[k] = warp_sum(E[k]);
+              named_bar_sync(1 + g, 128);        // previous readers of the exchange buffer are done
+              if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < R / 2; ++k) xch[q * 40 + k] = E[k];
+              }
+              named_bar_sync(1 + g, 128);
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) E[k] = (xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]);
+            }
+            // e_k = exp2(lambda ahat_k - lambda) <= 1 (|ahat| <= 1): no overflow in fp16 for any lambda.
+            // 1/(sqrt(S)+1e-8) = rsqrt(S) (1 - O(1e-8 rsqrt(S))): the shortcut is exact to 3e-4 relative
+            // for S >= 1e-9; below that (numerically orthogonal caption/region) take the exact form.
+            float smin = E[0];
+#pragma unroll
+            for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
+            const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && c.cap >= 0);
+            if (!exact) {
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) {
+                const float raw = A[18 * h + k];
+                const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
+                const float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
+                E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) {
+                const float raw = A[18 * h + k];
+                const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
+                const float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
+                E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
+              }
+            }
+            uint32_t hv[9];
+#pragma unroll
+            for (int cidx = 0; cidx < 9; ++cidx) hv[cidx] = pack_f16x2(E[2 * cidx], E[2 * cidx + 1]);
+            TMEM_ST_X8(te + 9 * h, hv, 0);
+            TMEM_ST_X1(te + 9 * h + 8, hv[8]);
+          }
+          {                                       // K is padded 36 -> 48: zero the last 6 columns
+            uint32_t z[4] = {0u, 0u, 0u, 0u};
+            TMEM_ST_X4(te + 18, z, 0);
+            TMEM_ST_X2(te + 22, z, 0);
+          }
+          c.P = P; c.D = Dd;
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(eready_bar(g));
+        }
+      }
     }
+    phase_b();                                    // drain
   }
 
   tc_fence_before();
@@ -638,6 +657,11 @@ prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out,
   // zero the padding rows / columns 36..47 of the fp16 block
   for (int e = threadIdx.x; e < G16_BYTES / 4; e += 256) reinterpret_cast<uint32_t*>(gp)[e] = 0u;
   __syncthreads();
+  // output column n = 36 is all ones over k < 36: U[:, 36] = sum_k e_k (the softmax denominator)
+  if (threadIdx.x < R) {
+    const int k2 = threadIdx.x;
+    reinterpret_cast<__half*>(gp)[(36 / 8) * (G_SBO / 2) + (k2 / 8) * (G_LBO / 2) + (36 % 8) * 8 + (k2 % 8)] = __float2half_rn(1.0f);
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __half* g16 = reinterpret_cast<__half*>(gp);
   float* gd = reinterpret_cast<float*>(gp + G16_BYTES);
@@ -766,6 +790,7 @@ static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_i
     scan_t2i_tc_kernel<true><<<1, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
   } else {
     long long total = (long long)p.n_wt * p.n_it;
+    if (total >= (1ll << 31)) return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tiles exceed the 2^31 scheduler range; split the call", total);
     int grid = (int)(total < sms ? total : sms);
     ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
     scan_t2i_tc_kernel<false><<<grid, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);

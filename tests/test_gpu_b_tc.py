@@ -69,7 +69,9 @@ def test_affinity_tile_matches_matmul():
                 dense[n_, k_] = g16[(n_ // 8) * 384 + (k_ // 8) * 64 + (n_ % 8) * 8 + (k_ % 8)]
         want = G[i] - np.eye(36)          # unit diagonal stays in fp32 on the CUDA cores (sum_k e_k^2)
         np.testing.assert_allclose(dense[:36, :36], want, rtol=1e-3, atol=1e-6)      # fp16 rounding
-        assert (dense[36:] == 0).all() and (dense[:, 36:] == 0).all()
+        # output column 36 is the all-ones vector over k < 36 (softmax denominator); the rest is zero padding
+        assert (dense[36, :36] == 1).all() and (dense[36, 36:] == 0).all()
+        assert (dense[37:] == 0).all() and (dense[:36, 36:] == 0).all()
 
 
 @pytest.mark.parametrize("case", ["scan_small", "scan_long"])
