@@ -71,8 +71,12 @@ constexpr int AUX_META = BLOCK_M * 16;             // 2048
 constexpr int AUX_WNORM = BLOCK_M * 4;             // 512
 constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 21568
 constexpr int XCH_FLOATS = 4 /*group*/ * 4 /*warp*/ * 40;
-constexpr int ACC_COLS = 144;                  // column stride between the two accumulators
-constexpr int U_BASE = 288;                    // four 48-column Gram-product buffers: [288, 480)
+// TMEM columns: [0,144) the accumulator (single buffer: it is released as soon as every epilogue
+// warp holds its 36 raw affinities in registers); [160,352) four 48-column Gram products U_g;
+// [352,472) four 24-column parking areas for the fp16 softmax numerators (32-column pitch).
+constexpr int U_BASE = 160;
+constexpr int PARK_BASE = 352;
+constexpr int PARK_PITCH = 32;
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 32;                       // word tiles kept L2-resident while images stream
 constexpr int NUM_THREADS = 640;
@@ -271,10 +275,6 @@ __device__ __forceinline__ float seg_total(float x, const bool (&p)[5], int seg_
   return __shfl_sync(0xffffffffu, x, seg_hi);
 }
 
-// column offset (inside an accumulator buffer) where image i's fp16 softmax numerators are parked:
-// 16-column aligned and inside the image's own 36 columns [36 i, 36 i + 36)
-__device__ __forceinline__ int e_col(int i) { return i == 0 ? 0 : 16 + 32 * i; }   // 0, 48, 80, 112
-
 // what phase B of an item needs from its phase A (phase B runs one item later, see below)
 struct Carry {
   float P, D, wnorm;
@@ -293,8 +293,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   const uint32_t bar0 = sbase + SMEM_BARS;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES + 0);
+  const uint32_t tempty_bar = bar0 + 8u * (2 * STAGES + 1);
   auto afull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };
   auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };
   auto eready_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 8 + g); };
@@ -307,10 +307,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS);
-      mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS);
-    }
+    mbar_init(tfull_bar, 1); mbar_init(tempty_bar, NUM_EPI_WARPS);
+    for (int b = 0; b < 2; ++b) { mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS); }
     for (int g = 0; g < IMGS; ++g) { mbar_init(eready_bar(g), 4); mbar_init(uready_bar(g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -355,10 +353,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int t = first; t < total; t += step, ++it) {
-      const int b = it & 1;
-      mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);
+      mbar_wait(tempty_bar, (it & 1) ^ 1);     // every epilogue warp has the previous tile in registers
       tc_fence_after();
-      const uint32_t tacc = tmem_base + b * ACC_COLS;
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -368,9 +364,9 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
           const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);   // +32 bytes per K step
+            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);   // +32 bytes per K step
           umma_commit(empty_bar(stage));
-          if (kb == K_BLOCKS - 1) umma_commit(tfull_bar(b));
+          if (kb == K_BLOCKS - 1) umma_commit(tfull_bar);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -394,7 +390,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
           mbar_wait(eready_bar(g), used[g]++ & 1);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t te = tmem_base + b * ACC_COLS + e_col(g);
+            const uint32_t te = tmem_base + PARK_BASE + g * PARK_PITCH;
             const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
             const uint64_t gdesc = umma_desc_nosw(aux + g * GRAM_BYTES, G_LBO, G_SBO);
 #pragma unroll
@@ -427,13 +423,17 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   }
   } else {
     // =============================== epilogue =============================================
-    // Group g (4 warps = all 128 word rows) owns image g of every tile.  Per item: phase B of the
-    // PREVIOUS item first (its Gram product has long landed), then phase A of the current one.
+    // Group g (4 warps = all 128 word rows) owns image g of every tile.  Per item:
+    //   A(t)   load the 36 raw affinities (accumulator released right away), l2norm scan, exp
+    //   B(t-1) finish the PREVIOUS item: its Gram product landed during A(t)
+    //   park(t) write e(t) as fp16 to the group's TMEM parking area, signal the Gram issuer
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int g = (warp - EPI_WARP0) >> 2;      // epilogue group = image of the tile
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t tu = tmem_base + U_BASE + g * GRAM_N + lane_sel;
+    const uint32_t tpark = tmem_base + PARK_BASE + g * PARK_PITCH + lane_sel;
     float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
     uint32_t used = 0u;                         // completed phases of uready[g]
     Carry c;
@@ -448,12 +448,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         tc_fence_after();
         float U[R];
         uint32_t hv[18];
-        const uint32_t tu = tmem_base + U_BASE + g * GRAM_N + lane_sel;
-        const uint32_t te = tmem_base + c.b * ACC_COLS + lane_sel + e_col(g);
         TMEM_LD_X32(tu, U, 0);
         TMEM_LD_X4(tu + 32, U, 32);
-        TMEM_LD_X16U(te, hv, 0);
-        TMEM_LD_X2U(te + 16, hv, 16);
+        TMEM_LD_X16U(tpark, hv, 0);
+        TMEM_LD_X2U(tpark + 16, hv, 16);
         float Zsum;
         TMEM_LD_X1F(tu + 36, Zsum);              // ones column of the Gram pack: sum_k e_k
         tmem_ld_wait();
@@ -479,6 +477,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         } else {
           float* x = xch + 36;
           tot = (p.agg == ITR_AGG_MAX) ? warp_max(v) : warp_sum(v);
+          named_bar_sync(1 + g, 128);
           if (lane == 0) x[q * 40] = tot;
           named_bar_sync(1 + g, 128);
           float t0 = x[0], t1 = x[40], t2 = x[80], t3 = x[120];
@@ -490,116 +489,119 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         if (writer && c.cap >= 0) p.scores[(size_t)c.img * p.ld + c.cap] = tot;
       }
       if (c.live) {
-        // every TMEM / SMEM read of that item is complete: hand its accumulator and aux buffers back
+        // the Gram MMA of that item has completed (or the image was a tail image): its aux buffer is free
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(tempty_bar(c.b)); mbar_arrive(aempty_bar(c.b)); }
+        if (lane == 0) mbar_arrive(aempty_bar(c.b));
       }
     };
 
     int it = 0;
     for (int t = first; t < total; t += step, ++it) {
-      phase_b();
-
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
       const int b = it & 1;
-      const uint32_t par = (it >> 1) & 1;
-      mbar_wait(afull_bar(b), par);
+      mbar_wait(afull_bar(b), (it >> 1) & 1);
       const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
       const int4 meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
-      c.wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
-      c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w; c.b = b; c.live = true;
-      c.img = n * IMGS + g;
-      c.valid = !DEBUG && c.img < p.n_img;
+      const float wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
       const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
       const bool long_tile = (meta.z >> 16) & 1;
+      const int img = n * IMGS + g;
+      const bool valid = !DEBUG && img < p.n_img;
 
-      mbar_wait(tfull_bar(b), par);
+      // ---------------- phase A(t): raw affinities -> registers, accumulator handed back ---------
+      mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + b * ACC_COLS + lane_sel;
-      if (DEBUG || c.valid) {
-        // ---------------- phase A: raw affinities -> softmax numerators, parked as fp16 ---------
-        float A[R];
-        TMEM_LD_X32(tacc + g * R, A, 0);
-        TMEM_LD_X4(tacc + g * R + 32, A, 32);
-        tmem_ld_wait();
-        if (DEBUG) {
+      float A[R];
+      TMEM_LD_X32(tmem_base + lane_sel + g * R, A, 0);
+      TMEM_LD_X4(tmem_base + lane_sel + g * R + 32, A, 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+      if (DEBUG) {
 #pragma unroll
-          for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + g * R + k] = A[k];
-        } else {
-          bool pr[5];
+        for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + g * R + k] = A[k];
+      }
+
+      uint32_t hv[18];
+      float P = 0.f, Dd = 0.f;
+      if (valid) {
+        bool pr[5];
 #pragma unroll
-          for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
-          float P = 0.f, Dd = 0.f;
-          const float shift = -fabsf(p.c_sm);
-          const uint32_t te = tacc + e_col(g);
+        for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
+        const float shift = -fabsf(p.c_sm);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {          // two halves of 18 regions: bounds the live registers
-            float E[R / 2];
+        for (int h = 0; h < 2; ++h) {          // two halves of 18 regions: bounds the live registers
+          float E[R / 2];
+#pragma unroll
+          for (int k = 0; k < R / 2; ++k) {
+            float a = p.clipped ? fmaxf(A[18 * h + k], 0.1f * A[18 * h + k]) : A[18 * h + k];
+            E[k] = a * a;
+          }
+          // l2norm denominators: sum over the caption's words of a^2, per region
+          if (!long_tile) {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
+          } else {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) E[k] = warp_sum(E[k]);
+            named_bar_sync(1 + g, 128);        // previous readers of the exchange buffer are done
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) xch[q * 40 + k] = E[k];
+            }
+            named_bar_sync(1 + g, 128);
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) E[k] = (xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]);
+          }
+          // e_k = exp2(lambda ahat_k - lambda) <= 1 (|ahat| <= 1): no overflow in fp16 for any lambda.
+          // 1/(sqrt(S)+1e-8) = rsqrt(S) (1 - O(1e-8 rsqrt(S))): the shortcut is exact to 3e-4 relative
+          // for S >= 1e-9; below that (numerically orthogonal caption/region) take the exact form.
+          float smin = E[0];
+#pragma unroll
+          for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
+          const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && meta.x >= 0);
+          if (!exact) {
 #pragma unroll
             for (int k = 0; k < R / 2; ++k) {
-              float a = p.clipped ? fmaxf(A[18 * h + k], 0.1f * A[18 * h + k]) : A[18 * h + k];
-              E[k] = a * a;
+              const float raw = A[18 * h + k];
+              const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
+              const float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
+              E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
             }
-            // l2norm denominators: sum over the caption's words of a^2, per region
-            if (!long_tile) {
+          } else {
 #pragma unroll
-              for (int k = 0; k < R / 2; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
-            } else {
-#pragma unroll
-              for (int k = 0; k < R / 2; ++k) E[k] = warp_sum(E[k]);
-              named_bar_sync(1 + g, 128);        // previous readers of the exchange buffer are done
-              if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < R / 2; ++k) xch[q * 40 + k] = E[k];
-              }
-              named_bar_sync(1 + g, 128);
-#pragma unroll
-              for (int k = 0; k < R / 2; ++k) E[k] = (xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]);
+            for (int k = 0; k < R / 2; ++k) {
+              const float raw = A[18 * h + k];
+              const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
+              const float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
+              E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
             }
-            // e_k = exp2(lambda ahat_k - lambda) <= 1 (|ahat| <= 1): no overflow in fp16 for any lambda.
-            // 1/(sqrt(S)+1e-8) = rsqrt(S) (1 - O(1e-8 rsqrt(S))): the shortcut is exact to 3e-4 relative
-            // for S >= 1e-9; below that (numerically orthogonal caption/region) take the exact form.
-            float smin = E[0];
-#pragma unroll
-            for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
-            const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && c.cap >= 0);
-            if (!exact) {
-#pragma unroll
-              for (int k = 0; k < R / 2; ++k) {
-                const float raw = A[18 * h + k];
-                const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
-                const float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
-                E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < R / 2; ++k) {
-                const float raw = A[18 * h + k];
-                const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
-                const float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
-                E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
-              }
-            }
-            uint32_t hv[9];
-#pragma unroll
-            for (int cidx = 0; cidx < 9; ++cidx) hv[cidx] = pack_f16x2(E[2 * cidx], E[2 * cidx + 1]);
-            TMEM_ST_X8(te + 9 * h, hv, 0);
-            TMEM_ST_X1(te + 9 * h + 8, hv[8]);
           }
-          {                                       // K is padded 36 -> 48: zero the last 6 columns
-            uint32_t z[4] = {0u, 0u, 0u, 0u};
-            TMEM_ST_X4(te + 18, z, 0);
-            TMEM_ST_X2(te + 22, z, 0);
-          }
-          c.P = P; c.D = Dd;
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(eready_bar(g));
+#pragma unroll
+          for (int cidx = 0; cidx < 9; ++cidx) hv[9 * h + cidx] = pack_f16x2(E[2 * cidx], E[2 * cidx + 1]);
         }
       }
+
+      // ---------------- phase B(t-1): the previous item's Gram product has landed by now ----------
+      phase_b();
+
+      // ---------------- park(t): e(t) as fp16 (K padded 36 -> 48 with zeros), wake the Gram issuer --
+      if (valid) {
+        uint32_t z[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        TMEM_ST_X16(tpark, hv, 0);
+        TMEM_ST_X2(tpark + 16, hv, 16);
+        TMEM_ST_X4(tpark + 18, z, 0);
+        TMEM_ST_X2(tpark + 22, z, 4);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(eready_bar(g));
+      }
+      c.P = P; c.D = Dd; c.wnorm = wnorm; c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w;
+      c.img = img; c.b = b; c.valid = valid; c.live = true;
     }
     phase_b();                                    // drain
   }
