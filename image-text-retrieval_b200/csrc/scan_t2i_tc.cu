@@ -42,6 +42,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace itr {
@@ -100,6 +102,14 @@ constexpr uint32_t IDESC_GRAM = (1u << 4) | ((uint32_t)(GRAM_N >> 3) << 17) | ((
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp.  Unlike `lane == 0`, the compiler knows the branch is entered by
+// exactly one thread with warp-uniform operands, so uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR)
+// are issued directly instead of through an ELECT/BRA.U.ANY uniformizing loop (measured: 187 -> N/2 clk per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -109,8 +119,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// try_wait suspends the thread in hardware until the phase completes or ~`hint_ns` elapse
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+// try_wait blocks in hardware for a short, implementation-defined time before it returns false.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// same with a suspend-time hint: the thread sleeps until the phase completes or ~hint_ns elapse.  Cheap in
+// issue slots, but the wake-up is slow (measured ~1-2K clk round trips on the operand ring), so only the
+// epilogue warps use it; the control warps spin.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -119,13 +141,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uin
       : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hang.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity, 20000u)) return;
+// Bounded waits: a protocol bug becomes a trap (reported as a CUDA error) instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {        // latency-critical: spin
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity, 20000u)) {
+  int n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {  // throughput warps: sleep
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_sleep(bar, parity, 20000u)) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+}
+// wait and add the cycles spent waiting to `acc` (profiling builds of the role loops)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+__device__ __forceinline__ void mbar_wait_sleep_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait_sleep(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait_sleep(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -262,6 +305,9 @@ struct Params {
   float* scores; long long ld;
   float* dump;                 // debug: raw affinities of item (dbg_m, dbg_n)
   int dbg_m, dbg_n;
+  long long* prof;             // optional [grid][16] cycle counters (see itr_scan_t2i_profile)
+  int ctrl_last;               // 1: the control warpgroup is the LAST one (highest warp ids), 0: the first
+  int skip_math;               // tuning only: epilogue loads and releases the accumulator, no arithmetic
 };
 
 // inclusive segmented scan over the lanes [seg_lo, lane], then broadcast of the segment total
@@ -288,7 +334,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // logical warp index: 0-3 control, 4-19 epilogue.  The shift is a multiple of 4, so the TMEM lane
+  // quarter (physical warp id % 4) and warpgroup alignment (setmaxnreg) are preserved.
+  const int warp = (int)((threadIdx.x >> 5) + (p.ctrl_last ? EPI_WARP0 : 0)) % (NUM_THREADS / 32);
+  const int lane = threadIdx.x & 31;
 
   const uint32_t bar0 = sbase + SMEM_BARS;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -321,6 +370,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  const bool prof_on = p.prof != nullptr;
   const Schedule sched(p.n_wt, p.n_it);
   const int total = DEBUG ? 1 : sched.total();
   const int first = DEBUG ? 0 : (int)blockIdx.x;
@@ -333,35 +383,42 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   if (warp == 0) {
     // =============================== TMA producer: operand ring ============================
     int stage = 0; uint32_t phase = 0;
+    long long w_empty = 0; const long long t_begin = clock64();
     for (int t = first; t < total; t += step) {
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        if (lane == 0) {
+        mbar_wait_sleep_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
+        if (elect_one()) {
           const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sa, &map_words, full_bar(stage), kb * BLOCK_K, m * BLOCK_M);
-          tma_load_2d(sa + A_BYTES, &map_imgs, full_bar(stage), kb * BLOCK_K, n * BLOCK_N);
+          if (p.skip_math & 2) {                 // tuning only: no operand traffic at all (stale SMEM)
+            mbar_arrive(full_bar(stage));
+          } else {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sa, &map_words, full_bar(stage), kb * BLOCK_K, m * BLOCK_M);
+            tma_load_2d(sa + A_BYTES, &map_imgs, full_bar(stage), kb * BLOCK_K, n * BLOCK_N);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 0] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1] = w_empty; }
   } else if (warp == 1) {
     // =============================== main MMA issuer ======================================
     int stage = 0; uint32_t phase = 0;
     int it = 0;
+    long long w_tempty = 0, w_full = 0; const long long t_begin = clock64();
     for (int t = first; t < total; t += step, ++it) {
-      mbar_wait(tempty_bar, (it & 1) ^ 1);     // every epilogue warp has the previous tile in registers
+      mbar_wait_sleep_t(tempty_bar, (it & 1) ^ 1, w_tempty, prof_on);     // every epilogue warp has the previous tile in registers
       tc_fence_after();
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_sleep_t(full_bar(stage), phase, w_full, prof_on);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+        const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);   // +32 bytes per K step
@@ -371,6 +428,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+    }
+    if (prof_on && lane == 0) {
+      p.prof[blockIdx.x * 16 + 2] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 3] = w_tempty; p.prof[blockIdx.x * 16 + 4] = w_full;
+      p.prof[blockIdx.x * 16 + 5] = it;
     }
   } else if (warp == 2) {
     // =============================== Gram MMA issuer =======================================
@@ -382,17 +443,17 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         int m, n;
         sched.map(t, m, n);
         const int b = it & 1;
-        mbar_wait(afull_bar(b), (it >> 1) & 1);
+        mbar_wait_sleep(afull_bar(b), (it >> 1) & 1);
         const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
 #pragma unroll
         for (int g = 0; g < IMGS; ++g) {
-          if (n * IMGS + g >= p.n_img) continue;
-          mbar_wait(eready_bar(g), used[g]++ & 1);
+          if (n * IMGS + g >= p.n_img || (p.skip_math & 1)) continue;
+          mbar_wait_sleep(eready_bar(g), used[g]++ & 1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t te = tmem_base + PARK_BASE + g * PARK_PITCH;
-            const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
-            const uint64_t gdesc = umma_desc_nosw(aux + g * GRAM_BYTES, G_LBO, G_SBO);
+          const uint32_t te = tmem_base + PARK_BASE + g * PARK_PITCH;
+          const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
+          const uint64_t gdesc = umma_desc_nosw(aux + g * GRAM_BYTES, G_LBO, G_SBO);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < GRAM_N / UMMA_K; ++k)          // 16 fp16 = 8 TMEM columns, 2 core matrices
               umma_f16_ts(tu, te + 8 * k, gdesc + (uint64_t)((2 * G_LBO * k) >> 4), IDESC_GRAM, k != 0);
@@ -409,8 +470,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
       const int b = it & 1;
-      mbar_wait(aempty_bar(b), ((it >> 1) & 1) ^ 1);
-      if (lane == 0) {
+      mbar_wait_sleep(aempty_bar(b), ((it >> 1) & 1) ^ 1);
+      if (elect_one()) {
         const int n_valid = min(IMGS, p.n_img - n * IMGS);
         const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
         mbar_expect_tx(afull_bar(b), n_valid * GRAM_BYTES + AUX_META + AUX_WNORM);
@@ -436,6 +497,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     const uint32_t tpark = tmem_base + PARK_BASE + g * PARK_PITCH + lane_sel;
     float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
     uint32_t used = 0u;                         // completed phases of uready[g]
+    long long w_tfull = 0, w_afull = 0, w_uready = 0; const long long t_begin = clock64();
     Carry c;
     c.live = false; c.valid = false; c.P = c.D = c.wnorm = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
 
@@ -444,7 +506,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       if (c.valid) {
         const int seg_lo = c.seg & 0xff, seg_hi = (c.seg >> 8) & 0xff;
         const bool long_tile = (c.seg >> 16) & 1;
-        mbar_wait(uready_bar(g), used++ & 1);
+        mbar_wait_sleep_t(uready_bar(g), used++ & 1, w_uready, prof_on);
         tc_fence_after();
         float U[R];
         uint32_t hv[18];
@@ -501,17 +563,17 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
       const int b = it & 1;
-      mbar_wait(afull_bar(b), (it >> 1) & 1);
+      mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
       const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
       const int4 meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
       const float wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
       const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
       const bool long_tile = (meta.z >> 16) & 1;
       const int img = n * IMGS + g;
-      const bool valid = !DEBUG && img < p.n_img;
+      const bool valid = !DEBUG && img < p.n_img && !(p.skip_math & 1);
 
       // ---------------- phase A(t): raw affinities -> registers, accumulator handed back ---------
-      mbar_wait(tfull_bar, it & 1);
+      mbar_wait_sleep_t(tfull_bar, it & 1, w_tfull, prof_on);
       tc_fence_after();
       float A[R];
       TMEM_LD_X32(tmem_base + lane_sel + g * R, A, 0);
@@ -604,6 +666,11 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       c.img = img; c.b = b; c.valid = valid; c.live = true;
     }
     phase_b();                                    // drain
+    if (prof_on && lane == 0 && q == 0) {
+      long long* o = p.prof + blockIdx.x * 16 + 6 + g * 2;      // groups 0..3 -> slots 6..13
+      o[0] = w_tfull + w_afull; o[1] = w_uready;
+      if (g == 0) { p.prof[blockIdx.x * 16 + 14] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 15] = w_afull; }
+    }
   }
 
   tc_fence_before();
@@ -689,6 +756,60 @@ prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out,
   }
 }
 
+// ---------------------------------------------------------------------------- tcgen05 microbenchmark
+// One CTA per SM issues `iters` kind::f16 MMAs (M = 128, K = 16) on whatever SMEM holds and reports
+// cycles per MMA.  Used to establish the cost model the tile shape was chosen on.
+//   n_cols : UMMA N (multiple of 16, <= 256)        n_acc : accumulators cycled through (1..3 with N <= 160)
+//   a_tmem : 1 = A operand from tensor memory (TS), 0 = from shared memory (SS)
+//   kadv   : 1 = walk the four K sub-steps of a 128-byte swizzle row like the real kernel, 0 = same address
+__global__ void __launch_bounds__(128, 1)
+mma_microbench_kernel(int n_cols, int n_acc, int iters, int a_tmem, int kadv, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  __shared__ uint32_t tmem_ptr;
+  __shared__ __align__(8) uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_ptr;
+  if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc = umma_desc_sw128(sbase), bdesc = umma_desc_sw128(sbase + 16384);
+    const long long t0 = clock64();
+    int acc = 0;
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t d = tbase + (uint32_t)(acc * 160);
+      const int k = kadv ? (i & 3) : 0;
+      if (elect_one()) {
+        if (a_tmem) umma_f16_ts(d, tbase + 480, bdesc + 2 * k, idesc, 1u);
+        else umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+      }
+      __syncwarp();
+      if (++acc == n_acc) acc = 0;
+    }
+    if (elect_one()) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -766,7 +887,7 @@ extern "C" int itr_scan_prep_images_bf16(const float* images, int n_img, int n_r
 static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
                      const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
                      float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, float* dump, int dbg_m,
-                     int dbg_n, void* stream) {
+                     int dbg_n, void* stream, long long* prof = nullptr, int mode = -1) {
   int rc = require_sm100();
   if (rc) return rc;
   CUtensorMap map_w, map_i;
@@ -783,7 +904,13 @@ static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_i
   p.c_sm = lambda_softmax * 1.4426950408889634f;
   p.c_lse = lambda_lse * 1.4426950408889634f;
   p.inv_lse = 0.6931471805599453f / lambda_lse;
-  p.scores = scores; p.ld = ld_scores; p.dump = dump; p.dbg_m = dbg_m; p.dbg_n = dbg_n;
+  p.scores = scores; p.ld = ld_scores; p.dump = dump; p.dbg_m = dbg_m; p.dbg_n = dbg_n; p.prof = prof;
+  {
+    static int env_ctrl_last = -1;
+    if (env_ctrl_last < 0) { const char* e = getenv("ITR_B200_CTRL_LAST"); env_ctrl_last = e ? atoi(e) : 1; }
+    p.ctrl_last = mode >= 0 ? (mode & 1) : env_ctrl_last;
+    p.skip_math = mode >= 0 ? ((mode >> 1) & 3) : 0;     // bit 0: no epilogue arithmetic, bit 1: no TMA operand loads
+  }
   int dev = 0, sms = 0;
   ITR_CHECK_CUDA(cudaGetDevice(&dev));
   ITR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -827,4 +954,25 @@ extern "C" int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_im
   return launch_tc(images_bf16, images_bf16, n_img, words_bf16,
                    reinterpret_cast<const int32_t*>(words_bf16), reinterpret_cast<const float*>(words_bf16), n_tiles,
                    ITR_NORM_CLIPPED_L2, ITR_AGG_SUM, 1.f, 1.f, out, 0, out, word_tile, image_tile, stream);
+}
+
+extern "C" int itr_scan_t2i_profile(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                                    const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                                    int n_tiles, float* scores, int64_t ld_scores, int64_t* counters, int mode, void* stream) {
+  ITR_REQUIRE(images_bf16 && gram_pack && words_bf16 && row_meta && row_wnorm && scores && counters, "itr_scan_t2i_profile: null pointer");
+  if (n_img <= 0 || n_tiles <= 0) return ITR_OK;
+  return launch_tc(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, ITR_NORM_CLIPPED_L2, ITR_AGG_LSE,
+                   9.f, 6.f, scores, ld_scores, nullptr, 0, 0, stream, reinterpret_cast<long long*>(counters), mode);
+}
+
+extern "C" int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_ctas, int64_t* cycles, void* stream) {
+  ITR_REQUIRE(cycles && n_cols >= 16 && n_cols <= 256 && n_cols % 16 == 0 && n_acc >= 1 && n_acc * 160 <= 480 && (n_acc == 1 || n_cols <= 160) && iters > 0 && n_ctas > 0,
+              "itr_tc_mma_microbench: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const int smem = 64 * 1024 + 1024;
+  ITR_CHECK_CUDA(cudaFuncSetAttribute(mma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_microbench_kernel<<<n_ctas, 128, smem, as_stream(stream)>>>(n_cols, n_acc, iters, a_tmem, kadv, reinterpret_cast<long long*>(cycles));
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
 }

@@ -108,6 +108,18 @@ int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const void* gram_pack,
 int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,
                                 int word_tile, int image_tile, float* out, void* stream);
 
+/* Debug / tuning: the score kernel (clipped_l2norm, LSE, lambda 9 / 6) with per-role wait-cycle counters,
+ * counters[cta][16] int64 (cta < #SMs): 0 producer total, 1 producer wait(empty), 2 MMA total, 3 MMA wait(tempty),
+ * 4 MMA wait(full), 5 items, 6+2g epilogue group g wait(tfull+afull), 7+2g wait(uready), 14 epilogue total, 15 wait(afull).
+ * mode bit 0: control warpgroup placed last (1) or first (0); bit 1: skip the epilogue arithmetic (scores are garbage). */
+int itr_scan_t2i_profile(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                         const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                         int n_tiles, float* scores, int64_t ld_scores, int64_t* counters, int mode, void* stream);
+
+/* Tuning: cycles for `iters` back-to-back tcgen05.mma (M=128, K=16, kind::f16) per CTA on `n_ctas` CTAs; see
+ * csrc/scan_t2i_tc.cu.  cycles[n_ctas]. */
+int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_ctas, int64_t* cycles, void* stream);
+
 /* ---- hinge loss: ContrastiveLoss.forward / TripletLoss.forward, Objectives.py:93-115, 492-517
  * loss (1 float, device) = sum of both directions; dscores (n x n, may be NULL) = dloss/dscores. */
 int itr_hinge_fwd_bwd_f32(const float* scores, int64_t ld_scores, int n, float margin, int max_violation,
