@@ -16,29 +16,27 @@
 // the identities  w_j . ctx_j = sum_k alpha_jk A[k][j]  and  |ctx_j|^2 = alpha_j^T G_i alpha_j
 // with G_i = V_i V_i^T the 36x36 region Gram, precomputed once per image.
 //
-// Kernel structure: persistent, warp-specialised, one CTA per SM.
+// Kernel structure: persistent, warp-specialised, one CTA per SM, 20 warps.
 //   tile       = 128 packed words (UMMA M) x 4 images = 144 region columns (UMMA N), K = 1024
-//   warp 0     TMA producer: 5-stage ring of {words 128x64, regions 144x64} bf16 tiles, SWIZZLE_128B,
-//              plus per-tile aux data (4 packed Grams, row metadata, word norms) by bulk copy
-//   warp 1     tcgen05.mma issuer (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM)
-//   warp 2     TMEM allocator (2 accumulator buffers of 144 columns + 4 Gram-product buffers)
-//   warps 2,3  issuers of the small "Gram" MMAs (one per epilogue group, see below)
-//   warps 4-11 epilogue, two groups of four warps; a group owns two of the tile's four images and
-//              all 128 word rows (thread = one word row = one TMEM lane):
-//                phase A(image): tcgen05.ld the 36 raw affinities -> leaky, l2norm over the
-//                  caption's words (segmented warp scan), e_k = exp2(lambda*ahat_k - lambda) in
-//                  registers; e is also written back, as fp16, over the image's now dead
-//                  accumulator columns (tcgen05.st) and a warp 2/3 thread issues
-//                  U = e . G_offdiag as a 128x48x48 tcgen05.mma with A FROM TMEM and the image's
-//                  fp16 Gram as the SMEM B operand;
-//                phase B(image): tcgen05.ld U, |ctx|^2 Z^2 = sum_k e_k U_k + sum_k G_kk e_k^2
-//                  (diagonal kept in fp32), cosine, aggregation over the caption's words.
-//              A(0) A(1) B(0) B(1) are software-pipelined so the Gram MMA latency is hidden.
-//              The two cross-row reductions (l2norm over the caption's words, aggregation over
-//              words) are segmented warp scans -- itr_scan_plan_words guarantees a caption never
-//              straddles a warp, except in `long` tiles which exchange through shared memory.
-// v1 of this kernel evaluated e^T G e on the CUDA cores from a broadcast SMEM copy of G: ncu showed
-// the SMEM data pipe 77% busy and the tensor pipe 22% (profiles/r01/ncu_v1_summary.txt).
+//   warp 0     TMA producer: 5-stage ring of {words 128x64, regions 144x64} bf16 tiles, SWIZZLE_128B
+//   warp 1     main tcgen05.mma issuer (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM)
+//   warp 2     TMEM allocator + issuer of the small "Gram" MMAs (see below)
+//   warp 3     aux loader: per-tile Gram packs, row metadata, word norms (bulk copies)
+//   warps 4-19 epilogue, four groups of four warps; group g owns image g of the tile and all 128 word
+//              rows (thread = one word row = one TMEM lane).  Per item:
+//                A(t)    tcgen05.ld the 36 raw affinities and hand the (single) accumulator straight back
+//                        to the MMA warp; leaky, l2norm over the caption's words (segmented warp scan),
+//                        e_k = exp2(lambda*ahat_k - lambda), P = sum e A, D = sum e^2;
+//                B(t-1)  finish the PREVIOUS item: tcgen05.ld U = e (G - I) and the parked fp16 e,
+//                        |ctx|^2 Z^2 = D + sum_k e_k U_k, cosine, aggregation over the caption's words, store;
+//                park(t) tcgen05.st e as fp16 into the group's TMEM parking area and wake the Gram issuer,
+//                        which runs U = e (G - I) as a 128x48x48 tcgen05.mma with A FROM TMEM and the
+//                        image's fp16 Gram pack as the SMEM B operand.
+//              The Gram product of item t therefore has a whole phase A to land: its latency is never exposed.
+//              The two cross-row reductions (l2norm over the caption's words, aggregation over words) are
+//              segmented warp scans -- itr_scan_plan_words guarantees a caption never straddles a warp,
+//              except in `long` tiles which exchange through shared memory.
+// History and measurements behind these choices: DESIGN.md section 5, profiles/r01/.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
