@@ -156,13 +156,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   }
 }
 // wait and add the cycles spent waiting to `acc` (profiling builds of the role loops)
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, const bool on) {
   if (!on) { mbar_wait(bar, parity); return; }
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += clock64() - t0;
 }
-__device__ __forceinline__ void mbar_wait_sleep_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+__device__ __forceinline__ void mbar_wait_sleep_t(uint32_t bar, uint32_t parity, long long& acc, const bool on) {
   if (!on) { mbar_wait_sleep(bar, parity); return; }
   const long long t0 = clock64();
   mbar_wait_sleep(bar, parity);
@@ -326,7 +326,7 @@ struct Carry {
   bool valid, live;
 };
 
-template <bool DEBUG>
+template <bool DEBUG, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -366,22 +366,25 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  // The CTA owns the SM (1 CTA/SM, all 512 columns allocated), so the allocation starts at column 0, lane 0.
+  // Treating the base as a compile-time constant keeps it out of the register file of the issuer warps.
+  if (*tmem_ptr_smem != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
-  const bool prof_on = p.prof != nullptr;
+  constexpr bool prof_on = PROF;         // wait-cycle counters are compiled out of the production kernel
   const Schedule sched(p.n_wt, p.n_it);
   const int total = DEBUG ? 1 : sched.total();
   const int first = DEBUG ? 0 : (int)blockIdx.x;
   const int step = DEBUG ? 1 : (int)gridDim.x;
 
   // Register budget: the control warpgroup (warps 0-3) gives registers back, the four epilogue
-  // warpgroups take them (128*40 + 512*104 <= 64K).
+  // warpgroups take them (128*56 + 512*104 <= 64K).
   if (warp < EPI_WARP0) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // =============================== TMA producer: operand ring ============================
     int stage = 0; uint32_t phase = 0;
-    long long w_empty = 0; const long long t_begin = clock64();
+    long long w_empty = 0; const long long t_begin = prof_on ? clock64() : 0;
     for (int t = first; t < total; t += step) {
       int m, n;
       if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
@@ -404,22 +407,29 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 0] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1] = w_empty; }
   } else if (warp == 1) {
     // =============================== main MMA issuer ======================================
+    // This warp shares its scheduler with four busy epilogue warps (measured: it is starved of issue
+    // slots, not the tensor pipe of work), so its per-k-block instruction count is kept minimal:
+    // descriptors are one 64-bit add away from a precomputed base.
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    long long w_tempty = 0, w_full = 0; const long long t_begin = clock64();
+    long long w_tempty = 0, w_full = 0; const long long t_begin = prof_on ? clock64() : 0;
+    const uint64_t adesc0 = umma_desc_sw128(sbase + SMEM_STAGES);
+    const uint64_t bdesc0 = umma_desc_sw128(sbase + SMEM_STAGES + A_BYTES);
+    const uint32_t tacc = tmem_base;
     for (int t = first; t < total; t += step, ++it) {
       mbar_wait_sleep_t(tempty_bar, (it & 1) ^ 1, w_tempty, prof_on);     // every epilogue warp has the previous tile in registers
       tc_fence_after();
+#pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
         mbar_wait_sleep_t(full_bar(stage), phase, w_full, prof_on);
         tc_fence_after();
-        const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+        const uint64_t soff = (uint64_t)((uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4));
+        const uint64_t adesc = adesc0 + soff, bdesc = bdesc0 + soff;
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);   // +32 bytes per K step
+          umma_bf16(tacc, adesc, bdesc, IDESC, (uint32_t)kb);                    // first MMA of a tile overwrites
+          umma_bf16(tacc, adesc + 2, bdesc + 2, IDESC, 1u);                      // +32 bytes per K step
+          umma_bf16(tacc, adesc + 4, bdesc + 4, IDESC, 1u);
+          umma_bf16(tacc, adesc + 6, bdesc + 6, IDESC, 1u);
           umma_commit(empty_bar(stage));
           if (kb == K_BLOCKS - 1) umma_commit(tfull_bar);
         }
@@ -495,7 +505,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     const uint32_t tpark = tmem_base + PARK_BASE + g * PARK_PITCH + lane_sel;
     float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
     uint32_t used = 0u;                         // completed phases of uready[g]
-    long long w_tfull = 0, w_afull = 0, w_uready = 0; const long long t_begin = clock64();
+    long long w_tfull = 0, w_afull = 0, w_uready = 0; const long long t_begin = prof_on ? clock64() : 0;
     Carry c;
     c.live = false; c.valid = false; c.P = c.D = c.wnorm = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
 
@@ -517,6 +527,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         tmem_ld_wait();
         // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form)
         float q0 = 0.f, q1 = 0.f;
+        if (!(p.skip_math & 16))
 #pragma unroll
         for (int cidx = 0; cidx < 18; ++cidx) {
           float2 ef = unpack_f16x2(hv[cidx]);
@@ -587,6 +598,16 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 
       uint32_t hv[18];
       float P = 0.f, Dd = 0.f;
+      if (p.skip_math & 32) {
+        // tuning only: pure register ALU work (no SMEM / TMEM / MUFU / SHFL), ~1150 dependent-free FMAs
+        float x0 = A[0], x1 = A[1], x2 = A[2], x3 = A[3];
+#pragma unroll 1
+        for (int r = 0; r < 36; ++r) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { x0 = fmaf(x0, 1.0001f, 0.5f); x1 = fmaf(x1, 1.0001f, 0.25f); x2 = fmaf(x2, 0.9999f, 0.125f); x3 = fmaf(x3, 0.9999f, 1.f); }
+        }
+        if (x0 + x1 + x2 + x3 == 123.456f) p.scores[0] = x0;
+      }
       if (valid) {
         bool pr[5];
 #pragma unroll
@@ -601,7 +622,9 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
             E[k] = a * a;
           }
           // l2norm denominators: sum over the caption's words of a^2, per region
-          if (!long_tile) {
+          if (p.skip_math & 4) {
+            // tuning only: no cross-lane reduction
+          } else if (!long_tile) {
 #pragma unroll
             for (int k = 0; k < R / 2; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
           } else {
@@ -623,7 +646,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 #pragma unroll
           for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
           const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && meta.x >= 0);
-          if (!exact) {
+          if (p.skip_math & 8) {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) { P += E[k]; }      // tuning only: no exp / rsqrt
+          } else if (!exact) {
 #pragma unroll
             for (int k = 0; k < R / 2; ++k) {
               const float raw = A[18 * h + k];
@@ -760,32 +786,37 @@ prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out,
 //   n_cols : UMMA N (multiple of 16, <= 256)        n_acc : accumulators cycled through (1..3 with N <= 160)
 //   a_tmem : 1 = A operand from tensor memory (TS), 0 = from shared memory (SS)
 //   kadv   : 1 = walk the four K sub-steps of a 128-byte swizzle row like the real kernel, 0 = same address
-__global__ void __launch_bounds__(128, 1)
-mma_microbench_kernel(int n_cols, int n_acc, int iters, int a_tmem, int kadv, long long* out) {
+__global__ void __launch_bounds__(192, 1)
+mma_microbench_kernel(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_issuers, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   __shared__ uint32_t tmem_ptr;
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ long long t_issuer[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_ptr;
-  if (warp == 1) {
+  if (warp >= 1 && warp <= n_issuers) {
+    const int w = warp - 1;                     // issuer w owns accumulators at columns w*... (n_acc * n_issuers * n_cols <= 480)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t adesc = umma_desc_sw128(sbase), bdesc = umma_desc_sw128(sbase + 16384);
     const long long t0 = clock64();
     int acc = 0;
     for (int i = 0; i < iters; ++i) {
-      const uint32_t d = tbase + (uint32_t)(acc * 160);
+      const uint32_t d = tbase + (uint32_t)((w * n_acc + acc) * n_cols);
       const int k = kadv ? (i & 3) : 0;
       if (elect_one()) {
         if (a_tmem) umma_f16_ts(d, tbase + 480, bdesc + 2 * k, idesc, 1u);
@@ -794,14 +825,19 @@ mma_microbench_kernel(int n_cols, int n_acc, int iters, int a_tmem, int kadv, lo
       __syncwarp();
       if (++acc == n_acc) acc = 0;
     }
-    if (elect_one()) umma_commit(smem_u32(&bar));
+    if (elect_one()) umma_commit(smem_u32(&bars[w]));
     __syncwarp();
-    mbar_wait(smem_u32(&bar), 0);
+    mbar_wait(smem_u32(&bars[w]), 0);
     const long long t1 = clock64();
-    if (lane == 0) out[blockIdx.x] = t1 - t0;
+    if (lane == 0) t_issuer[w] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    long long m = 0;
+    for (int i = 0; i < n_issuers; ++i) m = t_issuer[i] > m ? t_issuer[i] : m;
+    out[blockIdx.x] = m;
+  }
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
@@ -907,20 +943,25 @@ static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_i
     static int env_ctrl_last = -1;
     if (env_ctrl_last < 0) { const char* e = getenv("ITR_B200_CTRL_LAST"); env_ctrl_last = e ? atoi(e) : 1; }
     p.ctrl_last = mode >= 0 ? (mode & 1) : env_ctrl_last;
-    p.skip_math = mode >= 0 ? ((mode >> 1) & 3) : 0;     // bit 0: no epilogue arithmetic, bit 1: no TMA operand loads
+    p.skip_math = mode >= 0 ? ((mode >> 1) & 63) : 0;    // tuning bits: 1 no epilogue arithmetic, 2 no TMA loads, 4 no scan, 8 no exp, 16 no phase-B dot
   }
   int dev = 0, sms = 0;
   ITR_CHECK_CUDA(cudaGetDevice(&dev));
   ITR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (dump) {
-    ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    scan_t2i_tc_kernel<true><<<1, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
+    ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    scan_t2i_tc_kernel<true, false><<<1, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
   } else {
     long long total = (long long)p.n_wt * p.n_it;
     if (total >= (1ll << 31)) return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tiles exceed the 2^31 scheduler range; split the call", total);
     int grid = (int)(total < sms ? total : sms);
-    ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    scan_t2i_tc_kernel<false><<<grid, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
+    if (prof) {
+      ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+      scan_t2i_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
+    } else {
+      ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+      scan_t2i_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
+    }
   }
   ITR_CHECK_LAUNCH();
   return ITR_OK;
@@ -963,14 +1004,14 @@ extern "C" int itr_scan_t2i_profile(const uint16_t* images_bf16, const void* gra
                    9.f, 6.f, scores, ld_scores, nullptr, 0, 0, stream, reinterpret_cast<long long*>(counters), mode);
 }
 
-extern "C" int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_ctas, int64_t* cycles, void* stream) {
-  ITR_REQUIRE(cycles && n_cols >= 16 && n_cols <= 256 && n_cols % 16 == 0 && n_acc >= 1 && n_acc * 160 <= 480 && (n_acc == 1 || n_cols <= 160) && iters > 0 && n_ctas > 0,
-              "itr_tc_mma_microbench: bad arguments");
+extern "C" int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_issuers, int n_ctas, int64_t* cycles, void* stream) {
+  ITR_REQUIRE(cycles && n_cols >= 16 && n_cols <= 256 && n_cols % 16 == 0 && n_acc >= 1 && n_issuers >= 1 && n_issuers <= 4 &&
+              n_acc * n_issuers * n_cols <= 480 && iters > 0 && n_ctas > 0, "itr_tc_mma_microbench: bad arguments");
   int rc = require_sm100();
   if (rc) return rc;
   const int smem = 64 * 1024 + 1024;
   ITR_CHECK_CUDA(cudaFuncSetAttribute(mma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mma_microbench_kernel<<<n_ctas, 128, smem, as_stream(stream)>>>(n_cols, n_acc, iters, a_tmem, kadv, reinterpret_cast<long long*>(cycles));
+  mma_microbench_kernel<<<n_ctas, 192, smem, as_stream(stream)>>>(n_cols, n_acc, iters, a_tmem, kadv, n_issuers, reinterpret_cast<long long*>(cycles));
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }

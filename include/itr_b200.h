@@ -116,9 +116,9 @@ int itr_scan_t2i_profile(const uint16_t* images_bf16, const void* gram_pack, int
                          const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                          int n_tiles, float* scores, int64_t ld_scores, int64_t* counters, int mode, void* stream);
 
-/* Tuning: cycles for `iters` back-to-back tcgen05.mma (M=128, K=16, kind::f16) per CTA on `n_ctas` CTAs; see
- * csrc/scan_t2i_tc.cu.  cycles[n_ctas]. */
-int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_ctas, int64_t* cycles, void* stream);
+/* Tuning: cycles until `n_issuers` warps have each pushed `iters` tcgen05.mma (M=128, K=16, kind::f16) through the
+ * tensor pipe of one CTA, on `n_ctas` CTAs; see csrc/scan_t2i_tc.cu.  cycles[n_ctas]. */
+int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_issuers, int n_ctas, int64_t* cycles, void* stream);
 
 /* ---- hinge loss: ContrastiveLoss.forward / TripletLoss.forward, Objectives.py:93-115, 492-517
  * loss (1 float, device) = sum of both directions; dscores (n x n, may be NULL) = dloss/dscores. */
