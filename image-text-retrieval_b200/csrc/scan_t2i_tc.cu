@@ -277,17 +277,37 @@ struct Schedule {
     full_items = full_bands * BAND * n_it;
   }
   __device__ int total() const { return n_wt * n_it; }      // host guarantees < 2^31
-  __device__ void map(int t, int& m, int& n) const {
+  __device__ void map(int t, int& m, int& n, int& width, int& m_base) const {
     if (t < full_items) {
       int band = t / (BAND * n_it);
       int local = t - band * BAND * n_it;
       n = local / BAND;
-      m = band * BAND + local % BAND;
+      width = BAND; m_base = band * BAND;
+      m = m_base + local % BAND;
     } else {
       int local = t - full_items;
       n = local / last_band;
-      m = (n_wt - last_band) + local % last_band;
+      width = last_band; m_base = n_wt - last_band;
+      m = m_base + local % last_band;
     }
+  }
+};
+
+// Walks the items t, t + step, t + 2 step, ... of one CTA.  The (m, n) of the next item follows from the current
+// one with adds and compares; the divisions of Schedule::map run only when a band boundary is crossed.
+struct ItemIter {
+  const Schedule& s;
+  int t, step, m, n, width, m_base, dq, dr;
+  __device__ ItemIter(const Schedule& s_, int first, int step_) : s(s_), t(first), step(step_) { locate(); }
+  __device__ void locate() {
+    if (t < s.total()) { s.map(t, m, n, width, m_base); dq = step / width; dr = step - dq * width; }
+  }
+  __device__ bool valid() const { return t < s.total(); }
+  __device__ void next() {
+    t += step;
+    m += dr; n += dq;
+    if (m >= m_base + width) { m -= width; ++n; }
+    if (n >= s.n_it) locate();              // crossed into the next band (rare)
   }
 };
 
@@ -385,19 +405,19 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     // =============================== TMA producer: operand ring ============================
     int stage = 0; uint32_t phase = 0;
     long long w_empty = 0; const long long t_begin = prof_on ? clock64() : 0;
-    for (int t = first; t < total; t += step) {
-      int m, n;
-      if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
+    for (ItemIter item(sched, first, step); DEBUG ? item.t == first : item.valid(); item.next()) {
+      const int row_w = (DEBUG ? p.dbg_m : item.m) * BLOCK_M, row_i = (DEBUG ? p.dbg_n : item.n) * BLOCK_N;
+#pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
         mbar_wait_sleep_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
+        const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES, fb = full_bar(stage);
         if (elect_one()) {
-          const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
-          if (p.skip_math & 2) {                 // tuning only: no operand traffic at all (stale SMEM)
-            mbar_arrive(full_bar(stage));
+          if (PROF && (p.skip_math & 2)) {       // tuning only: no operand traffic at all (stale SMEM)
+            mbar_arrive(fb);
           } else {
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(sa, &map_words, full_bar(stage), kb * BLOCK_K, m * BLOCK_M);
-            tma_load_2d(sa + A_BYTES, &map_imgs, full_bar(stage), kb * BLOCK_K, n * BLOCK_N);
+            mbar_expect_tx(fb, STAGE_BYTES);
+            tma_load_2d(sa, &map_words, fb, kb * BLOCK_K, row_w);
+            tma_load_2d(sa + A_BYTES, &map_imgs, fb, kb * BLOCK_K, row_i);
           }
         }
         __syncwarp();
@@ -447,15 +467,14 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     if (!DEBUG) {
       int it = 0;
       uint32_t used[IMGS] = {0u, 0u, 0u, 0u};    // completed phases of eready[g] (tail images are skipped)
-      for (int t = first; t < total; t += step, ++it) {
-        int m, n;
-        sched.map(t, m, n);
+      for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
+        const int n = item.n;
         const int b = it & 1;
         mbar_wait_sleep(afull_bar(b), (it >> 1) & 1);
         const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
 #pragma unroll
         for (int g = 0; g < IMGS; ++g) {
-          if (n * IMGS + g >= p.n_img || (p.skip_math & 1)) continue;
+          if (n * IMGS + g >= p.n_img || (PROF && (p.skip_math & 1))) continue;
           mbar_wait_sleep(eready_bar(g), used[g]++ & 1);
           tc_fence_after();
           const uint32_t te = tmem_base + PARK_BASE + g * PARK_PITCH;
@@ -474,9 +493,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   } else {
     // =============================== aux loader: Gram packs, row metadata, word norms ======
     int it = 0;
-    for (int t = first; t < total; t += step, ++it) {
-      int m, n;
-      if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
+    for (ItemIter item(sched, first, step); DEBUG ? item.t == first : item.valid(); item.next(), ++it) {
+      const int m = DEBUG ? p.dbg_m : item.m, n = DEBUG ? p.dbg_n : item.n;
       const int b = it & 1;
       mbar_wait_sleep(aempty_bar(b), ((it >> 1) & 1) ^ 1);
       if (elect_one()) {
@@ -527,7 +545,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         tmem_ld_wait();
         // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form)
         float q0 = 0.f, q1 = 0.f;
-        if (!(p.skip_math & 16))
+        if (!(PROF && (p.skip_math & 16)))
 #pragma unroll
         for (int cidx = 0; cidx < 18; ++cidx) {
           float2 ef = unpack_f16x2(hv[cidx]);
@@ -568,9 +586,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     };
 
     int it = 0;
-    for (int t = first; t < total; t += step, ++it) {
-      int m, n;
-      if (DEBUG) { m = p.dbg_m; n = p.dbg_n; } else sched.map(t, m, n);
+    for (ItemIter item(sched, first, step); DEBUG ? item.t == first : item.valid(); item.next(), ++it) {
+      const int n = DEBUG ? p.dbg_n : item.n;
       const int b = it & 1;
       mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
       const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
@@ -579,7 +596,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
       const bool long_tile = (meta.z >> 16) & 1;
       const int img = n * IMGS + g;
-      const bool valid = !DEBUG && img < p.n_img && !(p.skip_math & 1);
+      const bool valid = !DEBUG && img < p.n_img && !(PROF && (p.skip_math & 1));
 
       // ---------------- phase A(t): raw affinities -> registers, accumulator handed back ---------
       mbar_wait_sleep_t(tfull_bar, it & 1, w_tfull, prof_on);
@@ -598,7 +615,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 
       uint32_t hv[18];
       float P = 0.f, Dd = 0.f;
-      if (p.skip_math & 32) {
+      if (PROF && (p.skip_math & 32)) {
         // tuning only: pure register ALU work (no SMEM / TMEM / MUFU / SHFL), ~1150 dependent-free FMAs
         float x0 = A[0], x1 = A[1], x2 = A[2], x3 = A[3];
 #pragma unroll 1
@@ -622,7 +639,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
             E[k] = a * a;
           }
           // l2norm denominators: sum over the caption's words of a^2, per region
-          if (p.skip_math & 4) {
+          if (PROF && (p.skip_math & 4)) {
             // tuning only: no cross-lane reduction
           } else if (!long_tile) {
 #pragma unroll
@@ -646,7 +663,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 #pragma unroll
           for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
           const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && meta.x >= 0);
-          if (p.skip_math & 8) {
+          if (PROF && (p.skip_math & 8)) {
 #pragma unroll
             for (int k = 0; k < R / 2; ++k) { P += E[k]; }      // tuning only: no exp / rsqrt
           } else if (!exact) {
