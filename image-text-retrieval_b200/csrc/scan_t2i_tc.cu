@@ -266,48 +266,37 @@ __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f3
 __device__ __forceinline__ float rsqf(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ---------------------------------------------------------------------------- tile schedule
-// Item t -> (word tile m, image tile n).  Word tiles are taken in bands of BAND; inside a band
-// the word tile varies fastest so the CTAs of one wave share a handful of image tiles and one
-// band of word tiles (both L2 resident) while the image set streams from HBM once per band.
+// Work unit = (band of BAND consecutive word tiles, image tile n); a CTA takes units u = cta, cta + grid, ...
+// and walks the band's word tiles against the SAME image tile.  So an image tile comes from HBM once per band
+// and is then re-read from L2 by the one CTA that owns it, while the band of word tiles (8 MB) stays L2-resident
+// and is shared by all CTAs.  (The first schedule let 32 CTAs request each image tile at the same instant: ncu
+// showed 159 GB of DRAM reads per COCO-5K launch against ~30 GB expected -- concurrent misses are not merged.)
 struct Schedule {
-  int n_wt, n_it, full_items, last_band;
+  int n_wt, n_it, n_bands, last_band;
   __device__ Schedule(int n_wt_, int n_it_) : n_wt(n_wt_), n_it(n_it_) {
-    int full_bands = n_wt / BAND;
-    last_band = n_wt - full_bands * BAND;
-    full_items = full_bands * BAND * n_it;
+    n_bands = (n_wt + BAND - 1) / BAND;
+    last_band = n_wt - (n_bands - 1) * BAND;
   }
-  __device__ int total() const { return n_wt * n_it; }      // host guarantees < 2^31
-  __device__ void map(int t, int& m, int& n, int& width, int& m_base) const {
-    if (t < full_items) {
-      int band = t / (BAND * n_it);
-      int local = t - band * BAND * n_it;
-      n = local / BAND;
-      width = BAND; m_base = band * BAND;
-      m = m_base + local % BAND;
-    } else {
-      int local = t - full_items;
-      n = local / last_band;
-      width = last_band; m_base = n_wt - last_band;
-      m = m_base + local % last_band;
-    }
-  }
+  __device__ int units() const { return n_bands * n_it; }   // host guarantees n_wt * n_it < 2^31
 };
 
-// Walks the items t, t + step, t + 2 step, ... of one CTA.  The (m, n) of the next item follows from the current
-// one with adds and compares; the divisions of Schedule::map run only when a band boundary is crossed.
+// Walks the items of one CTA: units u = first, first + step, ...; inside a unit the word tile advances.
 struct ItemIter {
   const Schedule& s;
-  int t, step, m, n, width, m_base, dq, dr;
-  __device__ ItemIter(const Schedule& s_, int first, int step_) : s(s_), t(first), step(step_) { locate(); }
-  __device__ void locate() {
-    if (t < s.total()) { s.map(t, m, n, width, m_base); dq = step / width; dr = step - dq * width; }
+  int u, step, m, n, left;
+  __device__ ItemIter(const Schedule& s_, int first, int step_) : s(s_), u(first), step(step_) { open(); }
+  __device__ void open() {
+    if (u < s.units()) {
+      const int band = u / s.n_it;
+      n = u - band * s.n_it;
+      m = band * BAND;
+      left = (band == s.n_bands - 1) ? s.last_band : BAND;
+    }
   }
-  __device__ bool valid() const { return t < s.total(); }
+  __device__ bool valid() const { return u < s.units(); }
   __device__ void next() {
-    t += step;
-    m += dr; n += dq;
-    if (m >= m_base + width) { m -= width; ++n; }
-    if (n >= s.n_it) locate();              // crossed into the next band (rare)
+    ++m;
+    if (--left == 0) { u += step; open(); }
   }
 };
 
@@ -393,7 +382,6 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 
   constexpr bool prof_on = PROF;         // wait-cycle counters are compiled out of the production kernel
   const Schedule sched(p.n_wt, p.n_it);
-  const int total = DEBUG ? 1 : sched.total();
   const int first = DEBUG ? 0 : (int)blockIdx.x;
   const int step = DEBUG ? 1 : (int)gridDim.x;
 
@@ -405,7 +393,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     // =============================== TMA producer: operand ring ============================
     int stage = 0; uint32_t phase = 0;
     long long w_empty = 0; const long long t_begin = prof_on ? clock64() : 0;
-    for (ItemIter item(sched, first, step); DEBUG ? item.t == first : item.valid(); item.next()) {
+    int dbg_it = 0;
+    for (ItemIter item(sched, first, step); DEBUG ? dbg_it == 0 : item.valid(); item.next(), ++dbg_it) {
       const int row_w = (DEBUG ? p.dbg_m : item.m) * BLOCK_M, row_i = (DEBUG ? p.dbg_n : item.n) * BLOCK_N;
 #pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
@@ -436,7 +425,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     const uint64_t adesc0 = umma_desc_sw128(sbase + SMEM_STAGES);
     const uint64_t bdesc0 = umma_desc_sw128(sbase + SMEM_STAGES + A_BYTES);
     const uint32_t tacc = tmem_base;
-    for (int t = first; t < total; t += step, ++it) {
+    for (ItemIter item(sched, first, step); DEBUG ? it == 0 : item.valid(); item.next(), ++it) {
       mbar_wait_sleep_t(tempty_bar, (it & 1) ^ 1, w_tempty, prof_on);     // every epilogue warp has the previous tile in registers
       tc_fence_after();
 #pragma unroll 1
@@ -493,7 +482,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   } else {
     // =============================== aux loader: Gram packs, row metadata, word norms ======
     int it = 0;
-    for (ItemIter item(sched, first, step); DEBUG ? item.t == first : item.valid(); item.next(), ++it) {
+    for (ItemIter item(sched, first, step); DEBUG ? it == 0 : item.valid(); item.next(), ++it) {
       const int m = DEBUG ? p.dbg_m : item.m, n = DEBUG ? p.dbg_n : item.n;
       const int b = it & 1;
       mbar_wait_sleep(aempty_bar(b), ((it >> 1) & 1) ^ 1);
@@ -586,7 +575,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     };
 
     int it = 0;
-    for (ItemIter item(sched, first, step); DEBUG ? item.t == first : item.valid(); item.next(), ++it) {
+    for (ItemIter item(sched, first, step); DEBUG ? it == 0 : item.valid(); item.next(), ++it) {
       const int n = DEBUG ? p.dbg_n : item.n;
       const int b = it & 1;
       mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
@@ -971,7 +960,8 @@ static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_i
   } else {
     long long total = (long long)p.n_wt * p.n_it;
     if (total >= (1ll << 31)) return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tiles exceed the 2^31 scheduler range; split the call", total);
-    int grid = (int)(total < sms ? total : sms);
+    long long units = (long long)((p.n_wt + BAND - 1) / BAND) * p.n_it;
+    int grid = (int)(units < sms ? units : sms);
     if (prof) {
       ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
       scan_t2i_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
