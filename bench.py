@@ -37,6 +37,17 @@ METRIC = "image-caption pair scores/sec (SCAN t2i COCO-5K eval)"
 R, D = 36, 1024
 
 
+def measured_traffic(n_img, n_cap, world):
+    """DRAM bytes per launch of the score kernel from the committed ncu capture (profiles/), or None."""
+    for rnd in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        path = os.path.join(ROOT, "profiles", rnd, "ncu_traffic.json")
+        if os.path.exists(path):
+            rec = json.load(open(path)).get("scan_t2i_tc_kernel", {}).get("{}x{}@{}".format(n_img, n_cap, world))
+            if rec:
+                return rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    return None
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -274,7 +285,10 @@ def main():
         "eval_wall_ms": {"device": ms_per_step, "e2e": e2e_s.item() * 1e3},
         "recall_check": {"i2t_r1": r1, "t2i_r1": r1_t, "e2e_rsum": res["rsum"]},
         "roofline": {"bound": "tensor", "kernel": "scan_t2i_tc_kernel", "achieved": achieved, "peak": pk["tflops"],
-                     "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                     "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": measured_traffic(n_img, n_cap, world),
+                     "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01/ncu_traffic.json); algorithmic minimum {:.2f} GB".format(
+                         (n_img * R * D * 2 + sum_words_local * D * 2 + n_img * (hi - lo) * 4) / 1e9),
+                     "peak_source": pk["src"],
                      "kernel_ms": kern_ms.item(), "algorithmic_flop_per_launch": f_alg,
                      "kernel_share_of_step": kern_ms.item() / ms_per_step},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -78,7 +78,7 @@ constexpr int U_BASE = 160;
 constexpr int PARK_BASE = 352;
 constexpr int PARK_PITCH = 32;
 constexpr int TMEM_COLS = 512;
-constexpr int BAND = 32;                       // word tiles kept L2-resident while images stream
+constexpr int BAND = 64;                       // word tiles kept L2-resident while images stream
 constexpr int NUM_THREADS = 640;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 16;
