@@ -206,7 +206,7 @@ def main():
     k_end = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
     def step(i=None):
-        pi = ops.prepare_images(images)
+        pi = ops.prepare_images_sharded(images, None, dev)      # each rank preps 1/N of the images + NCCL all-gather
         pc = ops.prepare_captions(captions, ln_local)
         if i is not None:
             k_start[i].record()
@@ -261,7 +261,7 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_img * n_cap / e2e_s.item()
     n_tiles = ops.plan_words(ln_local)[1]
-    h2d = n_img * R * D * 4 + sum_words_local * D * 4 + n_tiles * 128 * 16
+    h2d = -(-n_img // world) * R * D * 4 + sum_words_local * D * 4 + n_tiles * 128 * 16
     d2h = (n_img * 2 + n_cap * 2) * 8
 
     if rank != 0:
@@ -281,7 +281,7 @@ def main():
                    "n_img": n_img, "n_cap": n_cap, "sum_words": sum_words, "parallelism": "caption-shard x{}".format(world),
                    "l2_policy": "inputs larger than L2 (bf16 operands {:.0f} MB + {:.0f} MB score block per GPU)".format(
                        (n_img * R * D * 2 + n_tiles * 128 * D * 2) / 1e6, n_img * (hi - lo) * 4 / 1e6),
-                   "step": "prep(cast,pack,gram) + tcgen05 scores + rank kernels" + (" + rank exchange" if world > 1 else "")},
+                   "step": "prep(cast,pack,gram" + (", image shards all-gathered over NCCL" if world > 1 else "") + ") + tcgen05 scores + rank kernels" + (" + rank exchange" if world > 1 else "")},
         "eval_wall_ms": {"device": ms_per_step, "e2e": e2e_s.item() * 1e3},
         "recall_check": {"i2t_r1": r1, "t2i_r1": r1_t, "e2e_rsum": res["rsum"]},
         "roofline": {"bound": "tensor", "kernel": "scan_t2i_tc_kernel", "achieved": achieved, "peak": pk["tflops"],

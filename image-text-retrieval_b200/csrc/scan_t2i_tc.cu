@@ -737,51 +737,73 @@ pack_words_kernel(const float* __restrict__ captions, int lmax, int d, const int
   if (lane == 0) wnorm[row] = sqrtf(ss);
 }
 
-// One block per image: round the 36 regions to bf16 and build the image's Gram pack (fp16 off-diagonal
-// Gram in UMMA core-matrix order + fp32 diagonal) from the ROUNDED regions.
-__global__ void __launch_bounds__(256)
+// One block (192 threads) per image: round the 36 regions to bf16 and build the image's Gram pack (fp16
+// G - I in UMMA core-matrix order + fp32 diagonal + the ones row) from the ROUNDED regions.
+// The 36x36x1024 Gram is register-tiled: 144 threads each own a 3x3 block of G and sweep K from shared memory
+// (K-major rows with a 4-float skew -> conflict-free float4 reads); HBM-bound (6 B per element moved).
+constexpr int PREP_THREADS = 192;
+__global__ void __launch_bounds__(PREP_THREADS)
 prep_images_kernel(const float* __restrict__ images, uint16_t* __restrict__ out, uint8_t* __restrict__ gram_pack) {
   extern __shared__ float sv[];   // [R][D+4] rounded values
   constexpr int LD = D + 4;
   const float* src = images + (size_t)blockIdx.x * R * D;
   uint16_t* dst = out + (size_t)blockIdx.x * R * D;
   uint8_t* gp = gram_pack + (size_t)blockIdx.x * GRAM_BYTES;
-  for (int e = threadIdx.x; e < R * D / 4; e += 256) {
+  for (int e = threadIdx.x; e < R * D / 4; e += PREP_THREADS) {
     float4 x = reinterpret_cast<const float4*>(src)[e];
     uint16_t b0 = f32_to_bf16_rn(x.x), b1 = f32_to_bf16_rn(x.y), b2 = f32_to_bf16_rn(x.z), b3 = f32_to_bf16_rn(x.w);
     reinterpret_cast<uint2*>(dst)[e] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
     int r = (e * 4) / D, c = (e * 4) % D;
     *reinterpret_cast<float4*>(&sv[r * LD + c]) = make_float4(bf16_to_f32(b0), bf16_to_f32(b1), bf16_to_f32(b2), bf16_to_f32(b3));
   }
-  // zero the padding rows / columns 36..47 of the fp16 block
-  for (int e = threadIdx.x; e < G16_BYTES / 4; e += 256) reinterpret_cast<uint32_t*>(gp)[e] = 0u;
+  // zero the fp16 block (padding rows / columns 36..47), then the ones row n = 36 (U[:, 36] = sum_k e_k)
+  for (int e = threadIdx.x; e < G16_BYTES / 4; e += PREP_THREADS) reinterpret_cast<uint32_t*>(gp)[e] = 0u;
   __syncthreads();
-  // output column n = 36 is all ones over k < 36: U[:, 36] = sum_k e_k (the softmax denominator)
-  if (threadIdx.x < R) {
-    const int k2 = threadIdx.x;
-    reinterpret_cast<__half*>(gp)[(36 / 8) * (G_SBO / 2) + (k2 / 8) * (G_LBO / 2) + (36 % 8) * 8 + (k2 % 8)] = __float2half_rn(1.0f);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __half* g16 = reinterpret_cast<__half*>(gp);
   float* gd = reinterpret_cast<float*>(gp + G16_BYTES);
-  for (int o = warp; o < R * (R + 1) / 2; o += 8) {
-    int k = 0, rem = o;
-    while (rem > k) { rem -= k + 1; ++k; }     // o -> (k, k2 = rem), k2 <= k
-    const int k2 = rem;
-    const float* a = sv + k * LD;
-    const float* bq = sv + k2 * LD;
-    float s = 0.f;
-    for (int c = lane; c < D; c += 32) s = fmaf(a[c], bq[c], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (k == k2) {
-        gd[k] = s;
-        g16[(k / 8) * (G_SBO / 2) + (k / 8) * (G_LBO / 2) + (k % 8) * 8 + (k % 8)] = __float2half_rn(s - 1.0f);
-      } else {
-        const __half hs = __float2half_rn(s);
-        g16[(k / 8) * (G_SBO / 2) + (k2 / 8) * (G_LBO / 2) + (k % 8) * 8 + (k2 % 8)] = hs;
-        g16[(k2 / 8) * (G_SBO / 2) + (k / 8) * (G_LBO / 2) + (k2 % 8) * 8 + (k % 8)] = hs;
+  auto g16_at = [&](int n_, int k_) -> __half& { return g16[(n_ / 8) * (G_SBO / 2) + (k_ / 8) * (G_LBO / 2) + (n_ % 8) * 8 + (k_ % 8)]; };
+  if (threadIdx.x < R) g16_at(36, threadIdx.x) = __float2half_rn(1.0f);
+  if (threadIdx.x < 144) {
+    const int bi = threadIdx.x / 12, bj = threadIdx.x % 12;   // 12 x 12 blocks of 3 x 3
+    if (bj <= bi) {                                            // lower triangle of blocks (G is symmetric)
+      float4 acc4[3][3];                                       // four partial sums per output: accuracy + ILP
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc4[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* ra = sv + (3 * bi) * LD;
+      const float* rb = sv + (3 * bj) * LD;
+      for (int c = 0; c < D; c += 4) {
+        float4 a[3], bq[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { a[i] = *reinterpret_cast<const float4*>(ra + i * LD + c); bq[i] = *reinterpret_cast<const float4*>(rb + i * LD + c); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            acc4[i][j].x = fmaf(a[i].x, bq[j].x, acc4[i][j].x); acc4[i][j].y = fmaf(a[i].y, bq[j].y, acc4[i][j].y);
+            acc4[i][j].z = fmaf(a[i].z, bq[j].z, acc4[i][j].z); acc4[i][j].w = fmaf(a[i].w, bq[j].w, acc4[i][j].w);
+          }
       }
+      float acc[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j] = (acc4[i][j].x + acc4[i][j].y) + (acc4[i][j].z + acc4[i][j].w);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int k = 3 * bi + i, k2 = 3 * bj + j;
+          if (k == k2) {
+            gd[k] = acc[i][j];
+            g16_at(k, k) = __float2half_rn(acc[i][j] - 1.0f);
+          } else if (bi != bj || k2 < k) {
+            const __half hs = __float2half_rn(acc[i][j]);
+            g16_at(k, k2) = hs;
+            g16_at(k2, k) = hs;
+          }
+        }
     }
   }
 }
@@ -919,7 +941,7 @@ extern "C" int itr_scan_prep_images_bf16(const float* images, int n_img, int n_r
   if (n_img <= 0) return ITR_OK;
   const int smem = R * (D + 4) * 4;
   ITR_CHECK_CUDA(cudaFuncSetAttribute(prep_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  prep_images_kernel<<<n_img, 256, smem, as_stream(stream)>>>(images, images_bf16, reinterpret_cast<uint8_t*>(gram_pack));
+  prep_images_kernel<<<n_img, PREP_THREADS, smem, as_stream(stream)>>>(images, images_bf16, reinterpret_cast<uint8_t*>(gram_pack));
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }

@@ -50,8 +50,11 @@ def _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths):
     return ln
 
 
-def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False):
-    """The score matrix as a CUDA float32 tensor (n_img, n_cap); inputs host or device."""
+def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False,
+                image_group=None):
+    """The score matrix as a CUDA float32 tensor (n_img, n_cap); inputs host or device.
+    image_group: torch.distributed group over which the image preparation is sharded and all-gathered
+    (tensor-core SCAN path only; every rank passes the full image array and its own captions)."""
     dev = _device()
     config = model.config
     if config["name"] in ["CAMERA"]:
@@ -64,6 +67,21 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
     fused = cal_fun in (objectives.cosine_sim, objectives.xattn_score_t2i, objectives.xattn_score_i2t)
     with torch.no_grad():
         if fused:
+            norm_ = config.get("raw_feature_norm")
+            sharded = (image_group is not None and cal_fun is objectives.xattn_score_t2i
+                       and objectives._precision(config) == "bf16" and norm_ in ("clipped_l2norm", "l2norm")
+                       and getattr(img_embs, "ndim", 0) == 3 and tuple(img_embs.shape[1:]) == (36, 1024)
+                       and ln is not None and int(np.max(ln)) <= 128)
+            if sharded:
+                caps = cap_embs if isinstance(cap_embs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cap_embs))
+                if caps.dtype != torch.float32:
+                    caps = caps.float()
+                if not caps.is_cuda and not caps.is_pinned():
+                    caps = caps.to(dev)
+                pi = ops.prepare_images_sharded(img_embs, image_group, dev)
+                pc = ops.prepare_captions(caps, ln, device=dev)
+                return ops.scan_t2i_scores_bf16(pi, pc, norm_, config["agg_func"], config["lambda_softmax"],
+                                                config.get("lambda_lse", 6.0))
             img = _to_device(img_embs, dev)
             if cal_fun is objectives.cosine_sim:
                 return ops.cosine_scores(img, _to_device(cap_embs, dev))

@@ -124,6 +124,40 @@ def prepare_images(images) -> PreparedImages:
     return PreparedImages(out, gram, n_img)
 
 
+def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
+    """Multi-GPU form of prepare_images: every rank casts / Grams only its slice of the images (and, for host
+    input, uploads only that slice), then the bf16 regions and Gram packs are all-gathered over NVLink.
+    `images` is the FULL (n_img, 36, 1024) array on every rank: a host numpy array / tensor or a CUDA tensor."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+        return prepare_images(t.to(device if device is not None else "cuda", non_blocking=True))
+    rank = dist.get_rank(group)
+    n_img = len(images)
+    per = (n_img + world - 1) // world
+    lo, hi = min(rank * per, n_img), min((rank + 1) * per, n_img)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    sl = images[lo:hi]
+    if not isinstance(sl, torch.Tensor):
+        sl = torch.from_numpy(np.ascontiguousarray(sl))
+    sl = sl.to(dev, non_blocking=True)
+    img_all = torch.empty(world * per, capi.REGIONS, capi.EMBED, device=dev, dtype=torch.bfloat16)
+    gram_all = torch.empty(world * per, capi.GRAM_BYTES, device=dev, dtype=torch.uint8)
+    img_loc = img_all[rank * per:(rank + 1) * per]          # all_gather_into_tensor may gather in place
+    gram_loc = gram_all[rank * per:(rank + 1) * per]
+    if hi > lo:
+        loc = prepare_images(sl)
+        img_loc[: hi - lo].copy_(loc.images_bf16)
+        gram_loc[: hi - lo].copy_(loc.gram_pack)
+    if hi - lo < per:
+        img_loc[hi - lo:].zero_()
+        gram_loc[hi - lo:].zero_()
+    dist.all_gather_into_tensor(img_all, img_loc.clone(), group=group)
+    dist.all_gather_into_tensor(gram_all, gram_loc.clone(), group=group)
+    return PreparedImages(img_all[:n_img], gram_all[:n_img], n_img)
+
+
 def prepare_captions(captions, cap_lens, device=None) -> PreparedCaptions:
     """captions: CUDA f32 tensor, or a PINNED host f32 tensor (read in place over PCIe: only the
     true words of each caption cross the bus, not the zero padding)."""

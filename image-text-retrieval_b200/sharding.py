@@ -102,7 +102,10 @@ def sharded_scan_eval(images, captions_local, lengths_local, start, n_cap_total,
     from .objectives import ContrastiveLoss
     m.criterion = ContrastiveLoss(config, margin=config.get("margin", 0), measure=config.get("measure", "cosine"),
                                   max_violation=config.get("max_violation", False))
-    block = ev.device_sims(m, images, captions_local, lengths_local)
+    grp = group
+    if grp is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        grp = dist.group.WORLD
+    block = ev.device_sims(m, images, captions_local, lengths_local, image_group=grp)
     a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in
                   sharded_ranks(block, start, n_cap_total, group, caps_per_img)]
     res = ev._recall_dict(ev._metrics(a), (a, b), ev._metrics(c), (c, d), verbose=False)

@@ -62,7 +62,7 @@ def test_affinity_tile_matches_matmul():
     for i in (0, 10):
         g16 = pack[i, :4608].copy().view(np.float16).astype(np.float64)
         gd = pack[i, 4608:].copy().view(np.float32)
-        np.testing.assert_allclose(gd, np.diag(G[i]), rtol=1e-6)
+        np.testing.assert_allclose(gd, np.diag(G[i]), rtol=2e-6)        # fp32 accumulation of 1024 products
         dense = np.zeros((48, 48))
         for n_ in range(48):
             for k_ in range(48):
