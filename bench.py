@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-img", type=int, default=5000, help="override for debugging only (invalidates the number)")
     ap.add_argument("--n-cap", type=int, default=25000)
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config to measure; 5 (default) is the headline the driver runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-caps", type=int, default=300)
     return ap.parse_args()
@@ -167,8 +169,112 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _time_cuda(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_side_config(args):
+    """Configs 1-4 of BASELINE.json on one GPU (informational lines; the driver's contract is config 5)."""
+    import itr_b200
+    from itr_b200 import evaluation as ev, objectives as ob, ops, synth
+    from oracle import ref_port
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    out = {"config": args.config, "n_gpus": 1, "data": "synthetic", "cores": cores}
+    if args.config == 1:      # VSE++ cosine sim + i2t/t2i Recall@K, 1000 x 5000 x 1024
+        im, s = synth.vse_inputs(1000, 5000, 1, device=dev)
+        def dev_step():
+            return ev.device_ranks(ops.cosine_scores(im, s))
+        ms = _time_cuda(dev_step, 50)
+        im_h, s_h = im.cpu().numpy(), s.cpu().numpy()
+        class M: sim_enc = None
+        m = M(); m.config = dict(CONFIG, name="VSE++"); m.criterion = ob.ContrastiveLoss(m.config, 0.2, "cosine", True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            res = ev.cal_sims_and_recall(m, im_h, s_h)
+        e2e = (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        sims = ref_port.cosine_scores(torch.from_numpy(im_h), torch.from_numpy(s_h)).double().numpy()
+        ref_port.i2t_ranks(sims); ref_port.t2i_ranks(sims)
+        cpu = time.perf_counter() - t0
+        out.update(workload="VSE++ cosine + i2t/t2i Recall@K, 1000 img x 5000 caps x 1024 (fp32 kernels)", device_ms=ms,
+                   pairs_per_s=5e6 / (ms * 1e-3), e2e_ms=e2e * 1e3, cpu_port_ms=cpu * 1e3, rsum=res["rsum"])
+    elif args.config == 2:    # ContrastiveLoss max_violation, batch 128, embed 1024, fwd + bwd
+        im, s = synth.vse_inputs(128, 640, 2, device=dev)
+        s = s[::5].contiguous()
+        a, b = im.clone().requires_grad_(True), s.clone().requires_grad_(True)
+        crit = ob.ContrastiveLoss(dict(CONFIG, name="VSE++"), margin=0.2, measure="cosine", max_violation=True)
+        def ours():
+            a.grad = None; b.grad = None
+            crit(a, b).backward()
+        def eager():          # the reference's op sequence in eager PyTorch on the same GPU
+            a.grad = None; b.grad = None
+            sc = a.mm(b.t())
+            d = sc.diag().view(-1, 1)
+            eye = torch.eye(128, device=dev) > .5
+            cs = (0.2 + sc - d.expand_as(sc)).clamp(min=0).masked_fill_(eye, 0)
+            ci = (0.2 + sc - d.t().expand_as(sc)).clamp(min=0).masked_fill_(eye, 0)
+            (cs.max(1)[0].sum() + ci.max(0)[0].sum()).backward()
+        us_ours, us_eager = _time_cuda(ours, 300) * 1e3, _time_cuda(eager, 300) * 1e3
+        ac, bc = im.cpu().clone().requires_grad_(True), s.cpu().clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ac.grad = None; bc.grad = None
+            ref_port.hinge(ac.mm(bc.t()), 0.2, True).backward()
+        cpu = (time.perf_counter() - t0) / 50
+        out.update(workload="VSE++ ContrastiveLoss max_violation fwd+bwd, batch 128 x 1024", us_per_call=us_ours,
+                   us_per_call_eager_pytorch_same_gpu=us_eager, us_per_call_cpu_port=cpu * 1e6)
+    else:                     # SCAN 1000 x 5000 blocks
+        if args.config == 3:
+            shapes = [dict(synth.F30K_SHAPE)]
+            direction, agg, lam = "t2i", "LogSumExp", 9.0
+        else:
+            shapes = [dict(n_img=1000, n_cap=5000, lam=10.5, seed=14, fold=f) for f in range(5)]
+            direction, agg, lam = "i2t", "Mean", 4.0
+        cfg = dict(CONFIG, cross_attn=direction, agg_func=agg, lambda_softmax=lam)
+        tot_ms, tot_ms32, rsums = 0.0, 0.0, []
+        lens_all = synth.caption_lengths(25000, 10.5, 14)
+        for sh in shapes:
+            lengths = lens_all[sh["fold"] * 5000:(sh["fold"] + 1) * 5000] if "fold" in sh else None
+            img, cap, ln = synth.scan_inputs(sh["n_img"], sh["n_cap"], sh["lam"], sh["seed"] + sh.get("fold", 0), device=dev, lengths=lengths)
+            fn = ob.xattn_score_t2i if direction == "t2i" else ob.xattn_score_i2t
+            def dev_step(c=cfg):
+                return ev.device_ranks(fn(img, cap, ln, c))
+            tot_ms += _time_cuda(dev_step, 3, warmup=1)
+            if direction == "t2i":
+                tot_ms32 += _time_cuda(lambda: dev_step(dict(cfg, itr_b200_precision="fp32")), 1, warmup=1)
+            r = [x.cpu().numpy().astype(np.float64) for x in dev_step()]
+            rsums.append(sum(100.0 * np.mean(r[0] < k) + 100.0 * np.mean(r[2] < k) for k in (1, 5, 10)))
+        n_s, c_s = 1000, max(20, args.cpu_sample_caps // 3)
+        t0 = time.perf_counter()
+        ref_port.scan_scores(img[:n_s].cpu(), cap[:c_s].cpu(), ln[:c_s], direction, "clipped_l2norm", agg, lam, 6.0)
+        cpu_rate = n_s * c_s / (time.perf_counter() - t0)
+        pairs = sum(sh["n_img"] * sh["n_cap"] for sh in shapes)
+        out.update(workload="SCAN {} {} ({} block(s) of 1000 img x 5000 caps){}".format(
+                       direction, agg, len(shapes), ", tcgen05 bf16 path" if direction == "t2i" else ", fp32 CUDA-core path"),
+                   device_ms=tot_ms, pairs_per_s=pairs / (tot_ms * 1e-3), rsum=rsums,
+                   cpu_port_pairs_per_s=cpu_rate, cpu_sample="1000 img x {} caps".format(c_s))
+        if direction == "t2i":
+            out.update(device_ms_fp32_mode=tot_ms32)
+    print(json.dumps(out), flush=True)
+
+
 def main():
     args = parse()
+    if args.config != 5 and args.impl == "b200":
+        run_side_config(args)
+        return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -5,6 +5,7 @@
 //   - i2t / t2i rank counting                   (evaluation.py:156-222)
 // The throughput path for SCAN t2i lives in scan_t2i_tc.cu (tcgen05).
 #include <cfloat>
+#include <cstdlib>
 #include <cstdarg>
 
 #include "common.cuh"
@@ -28,29 +29,33 @@ int fail(int code, const char* fmt, ...) {
 // =========================================================================================
 // Generic strided SGEMM:  C[m][n] = sum_k A(m,k) * B(n,k)
 //   A(m,k) = A[m*a_rs + k*a_cs],  B(n,k) = B[n*b_rs + k*b_cs]
-// 64x64x16 block tile, 4x4 register tile, 256 threads.
+// TB x TB x 16 block tile, (TB/16) x (TB/16) register tile, 256 threads.  TB = 64 for large outputs,
+// TB = 32 when the output is so small (the 128 x 128 training batch) that 64-wide tiles would leave
+// the GPU with a handful of CTAs.
 // =========================================================================================
-constexpr int GB = 64, GK = 16;
+constexpr int GK = 16;
 
+template <int TB>
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs,
                      const float* __restrict__ B, int64_t b_rs, int64_t b_cs,
                      float* __restrict__ C, int64_t ldc, int M, int N, int K) {
-  __shared__ __align__(16) float As[GK][GB + 4];
-  __shared__ __align__(16) float Bs[GK][GB + 4];
+  constexpr int T = TB / 16;                       // register tile edge: 4 or 2
+  __shared__ __align__(16) float As[GK][TB + 4];
+  __shared__ __align__(16) float Bs[GK][TB + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const int m0 = blockIdx.y * TB, n0 = blockIdx.x * TB;
   const bool a_kfast = (a_cs == 1), b_kfast = (b_cs == 1);
-  float acc[4][4] = {};
+  float acc[T][T] = {};
   for (int k0 = 0; k0 < K; k0 += GK) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TB * GK / 256; ++i) {
       int e = tid + 256 * i;
-      int mm = a_kfast ? e / GK : e % GB, kk = a_kfast ? e % GK : e / GB;
+      int mm = a_kfast ? e / GK : e % TB, kk = a_kfast ? e % GK : e / TB;
       int gm = m0 + mm, gk = k0 + kk;
       As[kk][mm] = (gm < M && gk < K) ? A[gm * a_rs + gk * a_cs] : 0.f;
-      int nn = b_kfast ? e / GK : e % GB;
-      kk = b_kfast ? e % GK : e / GB;
+      int nn = b_kfast ? e / GK : e % TB;
+      kk = b_kfast ? e % GK : e / TB;
       int gn = n0 + nn;
       gk = k0 + kk;
       Bs[kk][nn] = (gn < N && gk < K) ? B[gn * b_rs + gk * b_cs] : 0.f;
@@ -58,23 +63,23 @@ sgemm_strided_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs,
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[T], bv[T];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < T; ++i) { av[i] = As[kk][ty * T + i]; bv[i] = Bs[kk][tx * T + i]; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < T; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < T; ++i) {
+    int gm = m0 + ty * T + i;
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
+    for (int j = 0; j < T; ++j) {
+      int gn = n0 + tx * T + j;
       if (gn < N) C[gm * ldc + gn] = acc[i][j];
     }
   }
@@ -82,8 +87,15 @@ sgemm_strided_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs,
 
 static int launch_sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
                         float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
-  dim3 grid((N + GB - 1) / GB, (M + GB - 1) / GB);
-  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K);
+  static int force_tb = -1;
+  if (force_tb < 0) { const char* e = getenv("ITR_B200_SGEMM_TB"); force_tb = e ? atoi(e) : 0; }
+  if (force_tb == 32 || (force_tb == 0 && (int64_t)M * N <= 256 * 1024)) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32);
+    sgemm_strided_kernel<32><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    sgemm_strided_kernel<64><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K);
+  }
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }

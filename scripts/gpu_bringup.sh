@@ -16,6 +16,7 @@ stage() {  # name, timeout, command...
 stage simt 900 python -m pytest tests/test_gpu_a_simt.py -x -q -m gpu
 stage tc_affinity 300 python -m pytest tests/test_gpu_b_tc.py -x -q -m gpu -k affinity
 stage tc_rest 900 python -m pytest tests/test_gpu_b_tc.py -q -m gpu -k "not affinity"
+stage fullsize 900 python -m pytest tests/test_gpu_c_fullsize.py -q -m gpu
 stage smoke 300 python __graft_entry__.py smoke
 stage bench_small 600 python bench.py --n-img 1000 --n-cap 5000 --steps 3 --warmup 2 --no-cpu-baseline
 stage bench_full 1200 python bench.py --steps 3 --warmup 3

@@ -1,0 +1,102 @@
+"""BASELINE.json's full sizes on the GPU, checked through size-independent properties (the oracle cannot
+finish these sizes in test time): agreement of the two independent CUDA paths on samples, oracle on a
+sub-block, run-to-run determinism, shard-count independence of every rank, and planted-structure recall."""
+import numpy as np
+import pytest
+import torch
+
+import itr_b200
+from itr_b200 import evaluation as ev, objectives as ob, ops, sharding
+from oracle import scan_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def cfg(**kw):
+    base = dict(name="SCAN", cross_attn="t2i", raw_feature_norm="clipped_l2norm", agg_func="LogSumExp",
+                lambda_lse=6.0, lambda_softmax=9.0, margin=0.2, max_violation=True, measure="cosine")
+    base.update(kw)
+    return base
+
+
+def virtual_shard_ranks(scores, world):
+    """Ranks computed shard by shard and merged exactly like the multi-GPU exchange (sum of counts, max of
+    thresholds / keys), on one device."""
+    n_img, n_cap = scores.shape
+    bounds = sharding.shard_bounds(n_cap, world)
+    thr = torch.full((n_img,), float("-inf"), device=scores.device)
+    for lo, hi in bounds:
+        t, _ = ops.rank_thresholds(scores[:, lo:hi], lo, 5)
+        thr = torch.maximum(thr, t)
+    i2t = torch.zeros(n_img, dtype=torch.int64, device=scores.device)
+    t2i = torch.zeros(n_cap, dtype=torch.int64, device=scores.device)
+    for lo, hi in bounds:
+        blk = scores[:, lo:hi]
+        _, tc = ops.rank_thresholds(blk, lo, 5)
+        cr, cc, _, _ = ops.rank_count(blk, thr, tc, lo)
+        i2t += cr.long()
+        t2i[lo:hi] = cc.long()
+    return i2t, t2i
+
+
+def test_config3_f30k_shape_full():
+    """SCAN t2i LSE, Flickr30K-shaped 1000 x 5000 (72 707 words)."""
+    sh = itr_b200.synth.F30K_SHAPE
+    img, cap, lens = itr_b200.synth.scan_inputs(device="cuda", round_to="bf16", **sh)
+    assert int(lens.sum()) == 72707
+    a = ob.xattn_score_t2i(img, cap, lens, cfg())
+    b = ob.xattn_score_t2i(img, cap, lens, cfg())
+    assert torch.equal(a, b)                                       # deterministic
+    assert torch.isfinite(a).all()
+    f32 = ob.xattn_score_t2i(img, cap[:400], lens[:400], cfg(itr_b200_precision="fp32"))
+    rel = ((a[:, :400] - f32).abs() / f32.abs().clamp_min(1e-6)).max().item()
+    assert rel < 1e-3, rel
+    want = so.scan_scores(img[:40].cpu().numpy(), cap[4000:4012].cpu().numpy(), lens[4000:4012], "t2i",
+                          "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    np.testing.assert_allclose(a[:40, 4000:4012].cpu().numpy(), want, rtol=1e-3, atol=1e-6)
+    i2t, _, t2i, _ = ev.device_ranks(a)
+    for world in (2, 8):
+        vi, vt = virtual_shard_ranks(a, world)
+        assert torch.equal(vi, i2t) and torch.equal(vt, t2i)
+    # the synthetic captions are planted on their image: recall must be high and ranks in range
+    assert (t2i < 1).float().mean().item() > 0.9 and (i2t < 10).float().mean().item() > 0.95
+    assert int(i2t.max()) < 5000 and int(t2i.max()) < 1000
+
+
+def test_config5_coco5k_shape_full():
+    """SCAN t2i LSE COCO-5K: 5000 x 25000 (312 906 words), plus the 8-way shard merge of the ranks."""
+    sh = itr_b200.synth.COCO5K_SHAPE
+    img, cap, lens = itr_b200.synth.scan_inputs(device="cuda", **sh)
+    assert int(lens.sum()) == 312906 and cap.shape == (25000, 72, 1024)
+    pi, pc = ops.prepare_images(img), ops.prepare_captions(cap, lens)
+    assert pc.n_tiles % 1 == 0 and pc.sum_len == 312906
+    a = ops.scan_t2i_scores_bf16(pi, pc, "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    assert torch.isfinite(a).all() and a.shape == (5000, 25000)
+    # a column block recomputed on its own (different packing, different tile schedule) is bit-identical
+    lo, hi = sharding.shard_bounds(25000, 8)[5]
+    pc_blk = ops.prepare_captions(cap[lo:hi], lens[lo:hi])
+    blk = ops.scan_t2i_scores_bf16(pi, pc_blk, "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    assert torch.equal(blk, a[:, lo:hi])
+    # fp32 CUDA-core path on a sample of captions incl. the planted long ones (every 997th)
+    cols = torch.tensor([0, 997, 1994, 12345, 24999], device="cuda")
+    f32 = ops.scan_scores_f32(img[:256], cap[cols], lens[cols.cpu().numpy()], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    rel = ((a[:256][:, cols] - f32).abs() / f32.abs().clamp_min(1e-6)).max().item()
+    assert rel < 1.5e-3, rel          # inputs here are NOT pre-rounded: bf16 input quantisation included
+    i2t, _, t2i, _ = ev.device_ranks(a)
+    vi, vt = virtual_shard_ranks(a, 8)
+    assert torch.equal(vi, i2t) and torch.equal(vt, t2i)
+    assert (t2i < 1).float().mean().item() > 0.9 and (i2t < 10).float().mean().item() > 0.9
+
+
+def test_config2_hinge_batch128_timing_sanity():
+    im, s = itr_b200.synth.vse_inputs(128, 640, 2, device="cuda")
+    s = s[::5].contiguous()
+    a, b = im.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    crit = ob.ContrastiveLoss(cfg(name="VSE++"), margin=0.2, measure="cosine", max_violation=True)
+    l1 = crit(a, b); l1.backward()
+    g1 = a.grad.clone()
+    a.grad = None; b.grad = None
+    l2 = crit(a, b); l2.backward()
+    assert l1.item() == l2.item() and torch.equal(g1, a.grad)     # deterministic loss and gradients
+    want, ds = so.hinge_loss(so.cosine_scores(im.cpu().numpy(), s.cpu().numpy()), 0.2, True)
+    np.testing.assert_allclose(l1.item(), want, rtol=1e-4)
