@@ -262,7 +262,7 @@ def run_side_config(args):
         cpu_rate = n_s * c_s / (time.perf_counter() - t0)
         pairs = sum(sh["n_img"] * sh["n_cap"] for sh in shapes)
         out.update(workload="SCAN {} {} ({} block(s) of 1000 img x 5000 caps){}".format(
-                       direction, agg, len(shapes), ", tcgen05 bf16 path" if direction == "t2i" else ", fp32 CUDA-core path"),
+                       direction, agg, len(shapes), ", fused tcgen05 bf16 kernel" if direction == "t2i" else ", tcgen05 bf16 affinities + fp32 epilogue kernel (two phases)"),
                    device_ms=tot_ms, pairs_per_s=pairs / (tot_ms * 1e-3), rsum=rsums,
                    cpu_port_pairs_per_s=cpu_rate, cpu_sample="1000 img x {} caps".format(c_s))
         if direction == "t2i":

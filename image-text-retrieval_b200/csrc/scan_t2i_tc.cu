@@ -335,7 +335,11 @@ struct Carry {
   bool valid, live;
 };
 
-template <bool DEBUG, bool PROF>
+// DEBUG: one (word tile, image tile) pair, raw accumulator to p.dump[128][144] (bring-up).
+// DUMP : the whole problem, raw affinities to p.dump[word tile][image][row][36] -- phase 1 of the generic
+//        two-phase path (itr_scan_affinity_bf16 + itr_scan_epilogue_f32) used for i2t and the norm modes the
+//        fused epilogue does not implement.  No Gram MMA, no aux loads, the epilogue is a TMEM -> HBM copy.
+template <bool DEBUG, bool PROF, bool DUMP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -453,7 +457,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   } else if (warp == 2) {
     // =============================== Gram MMA issuer =======================================
     // U_g = e_g (G_g - I): A = the group's parked fp16 numerators (TMEM), B = the image's Gram pack (SMEM)
-    if (!DEBUG) {
+    if (!DEBUG && !DUMP) {
       int it = 0;
       uint32_t used[IMGS] = {0u, 0u, 0u, 0u};    // completed phases of eready[g] (tail images are skipped)
       for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
@@ -482,6 +486,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   } else {
     // =============================== aux loader: Gram packs, row metadata, word norms ======
     int it = 0;
+    if (!DUMP)
     for (ItemIter item(sched, first, step); DEBUG ? it == 0 : item.valid(); item.next(), ++it) {
       const int m = DEBUG ? p.dbg_m : item.m, n = DEBUG ? p.dbg_n : item.n;
       const int b = it & 1;
@@ -578,14 +583,18 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     for (ItemIter item(sched, first, step); DEBUG ? it == 0 : item.valid(); item.next(), ++it) {
       const int n = DEBUG ? p.dbg_n : item.n;
       const int b = it & 1;
-      mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
-      const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
-      const int4 meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
-      const float wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
+      int4 meta = make_int4(-1, 0, 0, 0);
+      float wnorm = 0.f;
+      if (!DUMP) {
+        mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
+        const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
+        meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
+        wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
+      }
       const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
       const bool long_tile = (meta.z >> 16) & 1;
       const int img = n * IMGS + g;
-      const bool valid = !DEBUG && img < p.n_img && !(PROF && (p.skip_math & 1));
+      const bool valid = !DEBUG && !DUMP && img < p.n_img && !(PROF && (p.skip_math & 1));
 
       // ---------------- phase A(t): raw affinities -> registers, accumulator handed back ---------
       mbar_wait_sleep_t(tfull_bar, it & 1, w_tfull, prof_on);
@@ -600,6 +609,12 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       if (DEBUG) {
 #pragma unroll
         for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + g * R + k] = A[k];
+      }
+      if (DUMP && img < p.n_img) {
+        // [word tile][image][row][36]: a warp writes 32 rows x 144 bytes = 4.6 KB contiguous
+        float4* dst = reinterpret_cast<float4*>(p.dump + (((size_t)item.m * p.n_img + img) * BLOCK_M + row) * R);
+#pragma unroll
+        for (int k = 0; k < R; k += 4) dst[k / 4] = make_float4(A[k], A[k + 1], A[k + 2], A[k + 3]);
       }
 
       uint32_t hv[18];
@@ -693,7 +708,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         if (lane == 0) mbar_arrive(eready_bar(g));
       }
       c.P = P; c.D = Dd; c.wnorm = wnorm; c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w;
-      c.img = img; c.b = b; c.valid = valid; c.live = true;
+      c.img = img; c.b = b; c.valid = valid; c.live = !DUMP;
     }
     phase_b();                                    // drain
     if (prof_on && lane == 0 && q == 0) {
@@ -949,7 +964,7 @@ extern "C" int itr_scan_prep_images_bf16(const float* images, int n_img, int n_r
 static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
                      const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
                      float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, float* dump, int dbg_m,
-                     int dbg_n, void* stream, long long* prof = nullptr, int mode = -1) {
+                     int dbg_n, void* stream, long long* prof = nullptr, int mode = -1, bool full_dump = false) {
   int rc = require_sm100();
   if (rc) return rc;
   CUtensorMap map_w, map_i;
@@ -976,9 +991,16 @@ static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_i
   int dev = 0, sms = 0;
   ITR_CHECK_CUDA(cudaGetDevice(&dev));
   ITR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (dump) {
+  if (dump && !full_dump) {
     ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
     scan_t2i_tc_kernel<true, false><<<1, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
+  } else if (full_dump) {
+    long long total = (long long)p.n_wt * p.n_it;
+    if (total >= (1ll << 31)) return fail(ITR_ERR_INVALID, "itr_scan_affinity_bf16: %lld tiles exceed the 2^31 scheduler range; split the call", total);
+    long long units = (long long)((p.n_wt + BAND - 1) / BAND) * p.n_it;
+    int grid = (int)(units < sms ? units : sms);
+    ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_t2i_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    scan_t2i_tc_kernel<false, false, true><<<grid, NUM_THREADS, SMEM_ALLOC, as_stream(stream)>>>(map_w, map_i, p);
   } else {
     long long total = (long long)p.n_wt * p.n_it;
     if (total >= (1ll << 31)) return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tiles exceed the 2^31 scheduler range; split the call", total);
@@ -1043,4 +1065,15 @@ extern "C" int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tme
   mma_microbench_kernel<<<n_ctas, 192, smem, as_stream(stream)>>>(n_cols, n_acc, iters, a_tmem, kadv, n_issuers, reinterpret_cast<long long*>(cycles));
   ITR_CHECK_LAUNCH();
   return ITR_OK;
+}
+
+extern "C" int itr_scan_affinity_bf16(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,
+                                      float* affinity, void* stream) {
+  ITR_REQUIRE(images_bf16 && words_bf16 && affinity, "itr_scan_affinity_bf16: null pointer");
+  ITR_REQUIRE(((uintptr_t)images_bf16 & 15) == 0 && ((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)affinity & 15) == 0,
+              "itr_scan_affinity_bf16: buffers must be 16-byte aligned");
+  if (n_img <= 0 || n_tiles <= 0) return ITR_OK;
+  return launch_tc(images_bf16, images_bf16, n_img, words_bf16, reinterpret_cast<const int32_t*>(words_bf16),
+                   reinterpret_cast<const float*>(words_bf16), n_tiles, ITR_NORM_CLIPPED_L2, ITR_AGG_SUM, 1.f, 1.f, affinity, 0,
+                   affinity, 0, 0, stream, nullptr, -1, true);
 }

@@ -240,6 +240,107 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
 
 __device__ __forceinline__ float leaky01(float x) { return x > 0.f ? x : 0.1f * x; }
 
+struct ScanEpiParams {
+  int R, cross_attn, feature_norm, agg;
+  float lambda_softmax, lambda_lse;
+  float* scores; int64_t ld_scores;
+};
+
+// The reference's epilogue on a block-resident affinity tile (shared by the fp32 kernel and by phase 2 of the
+// tensor-core generic path).  Araw / X: [n_im * R rows][LP] (row = image-major region, column = word), X is scratch.
+// Gctx: t2i -> n_im region Grams (R x R each); i2t -> the caption's word Gram with row stride LP.
+__device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n_im, int n, int img0, int c, int LP,
+                                                   float* Araw, float* X, const float* Gctx, const float* wnorm,
+                                                   const float* vnorm, float* rsim, int RS) {
+  const int R = p.R, tid = threadIdx.x, nthr = blockDim.x;
+  const bool t2i = (p.cross_attn == ITR_T2I);
+  // index helpers: element (image m, source s, query q) of the [row][word] arrays
+  const int S = t2i ? R : n, Q = t2i ? n : R;
+  auto at = [&](float* base, int m, int s, int q) -> float& {
+    return t2i ? base[(m * R + s) * LP + q] : base[(m * R + q) * LP + s];
+  };
+
+  // ---- step 1: raw_feature_norm over q, for every (image, s) ---------------------------
+  for (int it = tid; it < n_im * S; it += nthr) {
+    int m = it / S, s = it % S;
+    const int mode = p.feature_norm;
+    if (mode == ITR_NORM_CLIPPED_L2 || mode == ITR_NORM_L2) {
+      float ss = 0.f;
+      for (int q = 0; q < Q; ++q) {
+        float a = at(Araw, m, s, q);
+        if (mode == ITR_NORM_CLIPPED_L2) a = leaky01(a);
+        ss = fmaf(a, a, ss);
+      }
+      float inv = 1.f / (sqrtf(ss) + 1e-8f);
+      for (int q = 0; q < Q; ++q) {
+        float a = at(Araw, m, s, q);
+        if (mode == ITR_NORM_CLIPPED_L2) a = leaky01(a);
+        at(X, m, s, q) = a * inv;
+      }
+    } else if (mode == ITR_NORM_SOFTMAX) {
+      float mx = -FLT_MAX;
+      for (int q = 0; q < Q; ++q) mx = fmaxf(mx, at(Araw, m, s, q));
+      float z = 0.f;
+      for (int q = 0; q < Q; ++q) z += expf(at(Araw, m, s, q) - mx);
+      float inv = 1.f / z;
+      for (int q = 0; q < Q; ++q) at(X, m, s, q) = expf(at(Araw, m, s, q) - mx) * inv;
+    } else {
+      for (int q = 0; q < Q; ++q) {
+        float a = at(Araw, m, s, q);
+        at(X, m, s, q) = (mode == ITR_NORM_CLIPPED) ? leaky01(a) : a;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- step 2+3: softmax over s, attended cosine, for every (image, q) -------------------
+  for (int it = tid; it < n_im * Q; it += nthr) {
+    int m = it / Q, q = it % Q;
+    float mx = -FLT_MAX;
+    for (int s = 0; s < S; ++s) mx = fmaxf(mx, at(X, m, s, q) * p.lambda_softmax);
+    float Z = 0.f, P = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float e = expf(at(X, m, s, q) * p.lambda_softmax - mx);
+      at(X, m, s, q) = e;
+      Z += e;
+      P = fmaf(e, at(Araw, m, s, q), P);
+    }
+    const float* G = t2i ? Gctx + m * R * R : Gctx;
+    const int gs = t2i ? R : LP;
+    float Qf = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float u = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) u = fmaf(G[s * gs + s2], at(X, m, s2, q), u);
+      Qf = fmaf(at(X, m, s, q), u, Qf);
+    }
+    float qn = t2i ? wnorm[q] : vnorm[m * R + q];
+    float invZ = 1.f / Z;
+    float w12 = P * invZ;
+    float w2 = sqrtf(fmaxf(Qf, 0.f)) * invZ;
+    rsim[m * RS + q] = w12 / fmaxf(qn * w2, 1e-8f);
+  }
+  __syncthreads();
+
+  // ---- step 4: aggregate over q, one warp per image --------------------------------------
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < n_im) {
+    const float* r = rsim + warp * RS;
+    float v;
+    if (p.agg == ITR_AGG_MAX) {
+      v = -FLT_MAX;
+      for (int q = lane; q < Q; q += 32) v = fmaxf(v, r[q]);
+      v = warp_max(v);
+    } else {
+      v = 0.f;
+      for (int q = lane; q < Q; q += 32) v += (p.agg == ITR_AGG_LSE) ? expf(r[q] * p.lambda_lse) : r[q];
+      v = warp_sum(v);
+      if (p.agg == ITR_AGG_LSE) v = logf(v) / p.lambda_lse;
+      if (p.agg == ITR_AGG_MEAN) v = v / (float)Q;
+    }
+    if (lane == 0) p.scores[(int64_t)(img0 + warp) * p.ld_scores + c] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 scan_f32_kernel(ScanF32Params p) {
   extern __shared__ __align__(16) float smem[];
@@ -280,90 +381,83 @@ scan_f32_kernel(ScanF32Params p) {
   }
   __syncthreads();
 
-  // index helpers: element (image m, source s, query q) of the [row][word] arrays
-  const int S = t2i ? R : n, Q = t2i ? n : R;
-  auto at = [&](float* base, int m, int s, int q) -> float& {
-    return t2i ? base[(m * R + s) * SF_LP + q] : base[(m * R + q) * SF_LP + s];
-  };
+  ScanEpiParams ep{R, p.cross_attn, p.feature_norm, p.agg, p.lambda_softmax, p.lambda_lse, p.scores, p.ld_scores};
+  scan_epilogue_smem(ep, n_im, n, img0, c, SF_LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
+}
 
-  // ---- step 1: raw_feature_norm over q, for every (image, s) ---------------------------
-  for (int it = tid; it < n_im * S; it += 256) {
-    int m = it / S, s = it % S;
-    const int mode = p.feature_norm;
-    if (mode == ITR_NORM_CLIPPED_L2 || mode == ITR_NORM_L2) {
-      float ss = 0.f;
-      for (int q = 0; q < Q; ++q) {
-        float a = at(Araw, m, s, q);
-        if (mode == ITR_NORM_CLIPPED_L2) a = leaky01(a);
-        ss = fmaf(a, a, ss);
-      }
-      float inv = 1.f / (sqrtf(ss) + 1e-8f);
-      for (int q = 0; q < Q; ++q) {
-        float a = at(Araw, m, s, q);
-        if (mode == ITR_NORM_CLIPPED_L2) a = leaky01(a);
-        at(X, m, s, q) = a * inv;
-      }
-    } else if (mode == ITR_NORM_SOFTMAX) {
-      float mx = -FLT_MAX;
-      for (int q = 0; q < Q; ++q) mx = fmaxf(mx, at(Araw, m, s, q));
-      float z = 0.f;
-      for (int q = 0; q < Q; ++q) z += expf(at(Araw, m, s, q) - mx);
-      float inv = 1.f / z;
-      for (int q = 0; q < Q; ++q) at(X, m, s, q) = expf(at(Araw, m, s, q) - mx) * inv;
-    } else {
-      for (int q = 0; q < Q; ++q) {
-        float a = at(Araw, m, s, q);
-        at(X, m, s, q) = (mode == ITR_NORM_CLIPPED) ? leaky01(a) : a;
-      }
-    }
+// =========================================================================================
+// Phase 2 of the tensor-core generic path: the same epilogue, fed with the raw affinities the tcgen05 kernel
+// dumped (itr_scan_affinity_bf16), layout [word tile][image][row][R].  One block = one caption x 4 images.
+// =========================================================================================
+struct ScanEpiKernelParams {
+  const float* affinity; int n_img;            // images in this chunk (= second dimension of the dump)
+  const int32_t* cap_row0; const int32_t* cap_lens; const int32_t* cap_ids; int n_ids; int LP;
+  const float* row_wnorm;                      // [packed rows]
+  const float* region_norm;                    // [n_img][R]
+  const float* region_gram;                    // t2i: [n_img][R][R]
+  const float* cap_gram; const int64_t* gram_off;   // i2t: packed n_c x n_c word Grams
+  ScanEpiParams e;
+};
+
+// 256 threads for i2t (4 images x 36 regions = 144 work items in the softmax step), 128 for t2i (4 x n words)
+__global__ void __launch_bounds__(256)
+scan_epilogue_kernel(ScanEpiKernelParams p) {
+  const int EPI_THREADS = blockDim.x;
+  extern __shared__ __align__(16) float smem[];
+  const int R = p.e.R, RT = SF_IMGS * R, LP = p.LP;
+  float* Araw = smem;
+  float* X = Araw + RT * LP;
+  float* Gctx = X + RT * LP;
+  const int g_floats = max(SF_IMGS * R * R, LP * LP);
+  float* wnorm = Gctx + g_floats;              // LP
+  float* vnorm = wnorm + LP;                   // RT
+  float* rsim = vnorm + RT;                    // SF_IMGS * RS
+  const int RS = max(R, LP);
+  const int c = p.cap_ids ? p.cap_ids[blockIdx.x] : (int)blockIdx.x;
+  const int img0 = blockIdx.y * SF_IMGS, tid = threadIdx.x;
+  const int n_im = min(SF_IMGS, p.n_img - img0);
+  const int n = p.cap_lens[c];
+  const int row0 = p.cap_row0[c];
+  const int tile = row0 / ITR_TILE_WORDS, r_in = row0 % ITR_TILE_WORDS;
+  const bool t2i = (p.e.cross_attn == ITR_T2I);
+  // affinities: global [tile][img][row][k] (k fastest) -> smem Araw[(m*R + k)*LP + j]
+  for (int e = tid; e < n_im * n * R; e += EPI_THREADS) {
+    int k = e % R, j = (e / R) % n, m = e / (R * n);
+    Araw[(m * R + k) * LP + j] = p.affinity[(((size_t)tile * p.n_img + img0 + m) * ITR_TILE_WORDS + r_in + j) * R + k];
   }
-  __syncthreads();
-
-  // ---- step 2+3: softmax over s, attended cosine, for every (image, q) -------------------
-  for (int it = tid; it < n_im * Q; it += 256) {
-    int m = it / Q, q = it % Q;
-    float mx = -FLT_MAX;
-    for (int s = 0; s < S; ++s) mx = fmaxf(mx, at(X, m, s, q) * p.lambda_softmax);
-    float Z = 0.f, P = 0.f;
-    for (int s = 0; s < S; ++s) {
-      float e = expf(at(X, m, s, q) * p.lambda_softmax - mx);
-      at(X, m, s, q) = e;
-      Z += e;
-      P = fmaf(e, at(Araw, m, s, q), P);
-    }
-    const float* G = t2i ? Gctx + m * R * R : Gctx;
-    const int gs = t2i ? R : SF_LP;
-    float Qf = 0.f;
-    for (int s = 0; s < S; ++s) {
-      float u = 0.f;
-      for (int s2 = 0; s2 < S; ++s2) u = fmaf(G[s * gs + s2], at(X, m, s2, q), u);
-      Qf = fmaf(at(X, m, s, q), u, Qf);
-    }
-    float qn = t2i ? wnorm[q] : vnorm[m * R + q];
-    float invZ = 1.f / Z;
-    float w12 = P * invZ;
-    float w2 = sqrtf(fmaxf(Qf, 0.f)) * invZ;
-    rsim[m * RS + q] = w12 / fmaxf(qn * w2, 1e-8f);
+  if (t2i) {
+    for (int e = tid; e < n_im * R * R; e += EPI_THREADS) Gctx[e] = p.region_gram[(size_t)img0 * R * R + e];
+  } else {
+    const float* g = p.cap_gram + p.gram_off[c];
+    for (int e = tid; e < n * n; e += EPI_THREADS) Gctx[(e / n) * LP + (e % n)] = g[e];
   }
+  for (int j = tid; j < n; j += EPI_THREADS) wnorm[j] = p.row_wnorm[row0 + j];
+  for (int e = tid; e < n_im * R; e += EPI_THREADS) vnorm[e] = p.region_norm[(size_t)img0 * R + e];
   __syncthreads();
+  scan_epilogue_smem(p.e, n_im, n, img0, c, LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
+}
 
-  // ---- step 4: aggregate over q, one warp per image --------------------------------------
-  const int warp = tid >> 5, lane = tid & 31;
-  if (warp < n_im) {
-    const float* r = rsim + warp * RS;
-    float v;
-    if (p.agg == ITR_AGG_MAX) {
-      v = -FLT_MAX;
-      for (int q = lane; q < Q; q += 32) v = fmaxf(v, r[q]);
-      v = warp_max(v);
-    } else {
-      v = 0.f;
-      for (int q = lane; q < Q; q += 32) v += (p.agg == ITR_AGG_LSE) ? expf(r[q] * p.lambda_lse) : r[q];
-      v = warp_sum(v);
-      if (p.agg == ITR_AGG_LSE) v = logf(v) / p.lambda_lse;
-      if (p.agg == ITR_AGG_MEAN) v = v / (float)Q;
+// Word Gram of every caption from the packed bf16 rows: gram[gram_off[c] + j*n + j2] = w_j . w_j2 (fp32 accumulate).
+__global__ void __launch_bounds__(128)
+caption_gram_kernel(const uint16_t* __restrict__ words, const int32_t* __restrict__ cap_row0, const int32_t* __restrict__ cap_lens,
+                    const int64_t* __restrict__ gram_off, int d, float* __restrict__ gram) {
+  const int c = blockIdx.x, n = cap_lens[c], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint16_t* W = words + (size_t)cap_row0[c] * d;
+  float* g = gram + gram_off[c];
+  for (int o = warp; o < n * (n + 1) / 2; o += 4) {
+    int j = 0, rem = o;
+    while (rem > j) { rem -= j + 1; ++j; }
+    const int j2 = rem;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(W + (size_t)j * d);
+    const uint32_t* b = reinterpret_cast<const uint32_t*>(W + (size_t)j2 * d);
+    float s = 0.f;
+    for (int v = lane; v < d / 2; v += 32) {
+      uint32_t x = a[v], y = b[v];
+      s = fmaf(__uint_as_float(x << 16), __uint_as_float(y << 16), s);
+      s = fmaf(__uint_as_float(x & 0xffff0000u), __uint_as_float(y & 0xffff0000u), s);
     }
-    if (lane == 0) p.scores[(int64_t)(img0 + warp) * p.ld_scores + c] = v;
+    s = warp_sum(s);
+    if (lane == 0) { g[j * n + j2] = s; g[j2 * n + j] = s; }
   }
 }
 
@@ -739,5 +833,42 @@ extern "C" int itr_rank_f64(const double* scores, int64_t ld_scores, int n_img, 
   cudaFreeAsync(thr_row, st);
   cudaFreeAsync(best_row, st);
   ITR_CHECK_CUDA(e);
+  return ITR_OK;
+}
+
+extern "C" int itr_scan_caption_gram_f32(const uint16_t* words_bf16, const int32_t* cap_row0, const int32_t* cap_lens,
+                                         const int64_t* gram_off, int n_cap, int d, float* gram, void* stream) {
+  ITR_REQUIRE(words_bf16 && cap_row0 && cap_lens && gram_off && gram, "itr_scan_caption_gram_f32: null pointer");
+  ITR_REQUIRE(d > 0 && d % 2 == 0, "itr_scan_caption_gram_f32: embed size must be even");
+  if (n_cap <= 0) return ITR_OK;
+  caption_gram_kernel<<<n_cap, 128, 0, as_stream(stream)>>>(words_bf16, cap_row0, cap_lens, gram_off, d, gram);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_scan_epilogue_f32(const float* affinity, int n_img, const int32_t* cap_row0, const int32_t* cap_lens,
+                                     const int32_t* cap_ids, int n_ids, int max_len, const float* row_wnorm,
+                                     const float* region_norm, const float* region_gram, const float* cap_gram,
+                                     const int64_t* gram_off, int cross_attn, int feature_norm, int agg,
+                                     float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, void* stream) {
+  ITR_REQUIRE(affinity && cap_row0 && cap_lens && row_wnorm && region_norm && scores, "itr_scan_epilogue_f32: null pointer");
+  ITR_REQUIRE(cross_attn == ITR_T2I || cross_attn == ITR_I2T, "unknown cross_attn: %d", cross_attn);
+  ITR_REQUIRE(feature_norm >= 0 && feature_norm <= ITR_NORM_NONE, "unknown first norm type: %d", feature_norm);
+  ITR_REQUIRE(agg >= 0 && agg <= ITR_AGG_SUM, "unknown aggfunc: %d", agg);
+  ITR_REQUIRE(cross_attn == ITR_I2T ? (cap_gram && gram_off) : (region_gram != nullptr), "itr_scan_epilogue_f32: missing Gram input");
+  ITR_REQUIRE(max_len >= 1 && max_len <= ITR_TILE_WORDS && n_ids >= 0, "itr_scan_epilogue_f32: bad shape");
+  if (n_img <= 0 || n_ids <= 0) return ITR_OK;
+  const int R = ITR_REGIONS, RT = SF_IMGS * R, LP = max_len + 1;
+  ScanEpiKernelParams p{affinity, n_img, cap_row0, cap_lens, cap_ids, n_ids, LP, row_wnorm, region_norm, region_gram, cap_gram, gram_off,
+                        ScanEpiParams{R, cross_attn, feature_norm, agg, lambda_softmax, lambda_lse, scores, ld_scores}};
+  int g_floats = SF_IMGS * R * R > LP * LP ? SF_IMGS * R * R : LP * LP;
+  int rs = R > LP ? R : LP;
+  size_t smem = sizeof(float) * (2 * (size_t)RT * LP + g_floats + LP + RT + SF_IMGS * rs);
+  ITR_REQUIRE(smem <= 227 * 1024, "itr_scan_epilogue_f32: caption of %d words needs %zu bytes of shared memory", max_len, smem);
+  ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_ids, (n_img + SF_IMGS - 1) / SF_IMGS);
+  ITR_REQUIRE(grid.y <= 65535, "itr_scan_epilogue_f32: more than %d images per call", 65535 * SF_IMGS);
+  scan_epilogue_kernel<<<grid, cross_attn == ITR_I2T ? 256 : 128, smem, as_stream(stream)>>>(p);
+  ITR_CHECK_LAUNCH();
   return ITR_OK;
 }

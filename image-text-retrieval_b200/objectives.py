@@ -2,10 +2,10 @@
 argument meaning and error behaviour; reference lines cited per symbol).
 
 Precision modes (config key ``itr_b200_precision`` or env ``ITR_B200_PRECISION``):
-  "bf16" (default where available)  tcgen05 tensor-core kernel: inputs rounded to bf16,
-          fp32 accumulate -- SCAN t2i with raw_feature_norm in {clipped_l2norm, l2norm},
-          36 regions, embed 1024.  Scores within 1e-3 relative of the reference fed the
-          same rounded inputs.
+  "bf16" (default where available)  tensor-core paths for 36 regions x embed 1024: inputs rounded to
+          bf16, fp32 accumulate.  SCAN t2i with raw_feature_norm in {clipped_l2norm, l2norm} runs the
+          fused tcgen05 kernel; i2t and the other norm modes run tcgen05 affinities + an fp32 epilogue
+          kernel.  Scores within 1e-3 relative of the reference fed the same rounded inputs.
   "fp32"  CUDA-core float32 kernels: every mode / direction, within 1e-5 relative.
 Anything the bf16 kernel does not cover runs in fp32 mode -- on the GPU, never on the CPU.
 """
@@ -86,12 +86,16 @@ def _scan(images, captions, cap_lens, config, cross_attn):
         # the reference raises NameError here (undefined l1norm_d, defect D4)
         raise ValueError("raw_feature_norm {!r} is not implemented by the reference either".format(norm))
     images, captions = images.detach(), captions.detach()
-    if cross_attn == "t2i" and _precision(config) == "bf16" and ops.tc_supported(images, captions, norm):
+    if _precision(config) == "bf16" and ops.tc_shapes(images, captions) and norm in ("clipped_l2norm", "l2norm", "softmax", "clipped", "no_norm"):
         ln = ops.lengths_to_numpy(cap_lens, captions.size(0))
-        if ln.max(initial=0) <= 128:
-            pi = ops.prepare_images(images)
-            pc = ops.prepare_captions(captions, ln)
-            return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, lam_sm, lam_lse)
+        if 1 <= ln.min(initial=1) and ln.max(initial=0) <= 128:
+            if cross_attn == "t2i" and norm in ("clipped_l2norm", "l2norm"):
+                pi = ops.prepare_images(images)
+                pc = ops.prepare_captions(captions, ln)
+                return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, lam_sm, lam_lse)      # fused tcgen05 kernel
+            if ln.max(initial=0) <= ops.GENERIC_MAX_WORDS:
+                # i2t and the remaining norm modes: tcgen05 affinities + fp32 epilogue (two phases)
+                return ops.scan_scores_tc_generic(images, captions, ln, cross_attn, norm, agg, lam_sm, lam_lse)
     return ops.scan_scores_f32(images, captions, cap_lens, cross_attn, norm, agg, lam_sm, lam_lse)
 
 

@@ -92,11 +92,18 @@ class PreparedCaptions:
     sum_len: int
 
 
-def tc_supported(images, captions, raw_feature_norm, cap_lens=None):
-    """Shapes / modes the tcgen05 kernel is built for."""
+GENERIC_MAX_WORDS = 100      # longest caption whose phase-2 tile fits in shared memory (2*144*(n+1) + (n+1)^2 floats)
+
+
+def tc_shapes(images, captions):
+    """Shapes the tcgen05 main loop is built for: 36 regions x embed 1024."""
     return (images.dim() == 3 and captions.dim() == 3 and images.size(1) == capi.REGIONS
-            and images.size(2) == capi.EMBED and captions.size(2) == capi.EMBED
-            and raw_feature_norm in ("clipped_l2norm", "l2norm"))
+            and images.size(2) == capi.EMBED and captions.size(2) == capi.EMBED)
+
+
+def tc_supported(images, captions, raw_feature_norm, cap_lens=None):
+    """Shapes / modes the FUSED tcgen05 t2i kernel is built for."""
+    return tc_shapes(images, captions) and raw_feature_norm in ("clipped_l2norm", "l2norm")
 
 
 def plan_words(lengths: np.ndarray):
@@ -197,6 +204,72 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
                                                   ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, norm, agg,
                                                   float(lambda_softmax), float(lambda_lse), ptr(out),
                                                   out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))
+    return out
+
+
+def caption_rows(pc: PreparedCaptions, lengths):
+    """cap_row0[c] = packed row index of caption c's first word (a caption's words are consecutive packed rows)."""
+    meta = pc.row_meta
+    first = (meta[:, 0] >= 0) & (meta[:, 1] == 0)
+    rows = torch.nonzero(first, as_tuple=False).flatten().to(torch.int32)
+    cap_row0 = torch.empty(pc.n_cap, device=meta.device, dtype=torch.int32)
+    cap_row0[meta[rows.long(), 0].long()] = rows
+    return cap_row0
+
+
+def scan_scores_tc_generic(images, captions, cap_lens, cross_attn, raw_feature_norm, agg_func, lambda_softmax, lambda_lse,
+                           pi: PreparedImages = None, pc: PreparedCaptions = None, max_affinity_bytes=6 << 30):
+    """Two-phase tensor-core path for everything the fused t2i kernel does not cover (i2t, softmax / clipped /
+    no_norm feature norms): tcgen05 affinities dumped per image chunk (itr_scan_affinity_bf16), then the reference's
+    epilogue in fp32 (itr_scan_epilogue_f32).  Inputs are rounded to bf16 for the D-wide contraction only."""
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    if cross_attn not in ("t2i", "i2t"):
+        raise ValueError("unknown cross_attn: {}".format(cross_attn))
+    if pi is None:
+        pi = prepare_images(images)
+    ln = lengths_to_numpy(cap_lens, len(cap_lens))
+    if pc is None:
+        pc = prepare_captions(captions, ln)
+    dev = pi.images_bf16.device
+    L = capi.lib()
+    n_img, n_cap = pi.n_img, pc.n_cap
+    out = torch.empty(n_img, n_cap, device=dev, dtype=torch.float32)
+    if n_img == 0 or n_cap == 0:
+        return out
+    cap_row0 = caption_rows(pc, ln)
+    lens_dev = torch.from_numpy(ln).to(dev)
+    # length classes: the phase-2 kernels are sized by the longest caption of a launch
+    classes = []
+    for lo_len, hi_len in ((1, 8), (9, 12), (13, 16), (17, 24), (25, 32), (33, 64), (65, GENERIC_MAX_WORDS)):
+        ids = np.nonzero((ln >= lo_len) & (ln <= hi_len))[0].astype(np.int32)
+        if len(ids):
+            classes.append((torch.from_numpy(ids).to(dev), len(ids), int(ln[ids].max())))
+    region_norm = pi.gram_pack[:, 4608:].contiguous().view(torch.float32).sqrt().contiguous()      # |v_k| from the Gram diagonal
+    cap_gram = gram_off = None
+    with torch.cuda.device(dev):
+        if cross_attn == "i2t":
+            off = np.zeros(n_cap + 1, dtype=np.int64)
+            np.cumsum(ln.astype(np.int64) ** 2, out=off[1:])
+            gram_off = torch.from_numpy(off[:-1].copy()).to(dev)
+            cap_gram = torch.empty(int(off[-1]), device=dev, dtype=torch.float32)
+            check(L.itr_scan_caption_gram_f32(ptr(pc.words_bf16), ptr(cap_row0), ptr(lens_dev), ptr(gram_off), n_cap, capi.EMBED,
+                                              ptr(cap_gram), stream_ptr()))
+        per_img = pc.n_tiles * capi.TILE_WORDS * capi.REGIONS * 4
+        chunk = max(capi.TILE_IMAGES, min(n_img, int(max_affinity_bytes // per_img)) // capi.TILE_IMAGES * capi.TILE_IMAGES)
+        aff = torch.empty(pc.n_tiles * chunk * capi.TILE_WORDS * capi.REGIONS, device=dev, dtype=torch.float32)
+        for i0 in range(0, n_img, chunk):
+            i1 = min(i0 + chunk, n_img)
+            check(L.itr_scan_affinity_bf16(ptr(pi.images_bf16[i0:i1]), i1 - i0, ptr(pc.words_bf16), pc.n_tiles, ptr(aff), stream_ptr()))
+            rgram = None
+            if cross_attn == "t2i":
+                rgram = torch.empty(i1 - i0, capi.REGIONS, capi.REGIONS, device=dev, dtype=torch.float32)
+                rounded = pi.images_bf16[i0:i1].float()
+                check(L.itr_region_gram_f32(ptr(rounded), i1 - i0, capi.REGIONS, capi.EMBED, ptr(rgram), stream_ptr()))
+            for ids, n_ids, max_len in classes:
+                check(L.itr_scan_epilogue_f32(ptr(aff), i1 - i0, ptr(cap_row0), ptr(lens_dev), ptr(ids), n_ids, max_len,
+                                              ptr(pc.row_wnorm), ptr(region_norm[i0:i1]), ptr(rgram), ptr(cap_gram), ptr(gram_off),
+                                              capi.T2I if cross_attn == "t2i" else capi.I2T, norm, agg, float(lambda_softmax),
+                                              float(lambda_lse), ptr(out[i0:i1]), out.stride(0), stream_ptr()))
     return out
 
 

@@ -103,6 +103,26 @@ int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const void* gram_pack,
                              const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                              int n_tiles, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                              float* scores, int64_t ld_scores, void* stream);
+/* ---- SCAN scores, generic two-phase tensor-core path (both directions, all raw_feature_norm modes) --------
+ * Phase 1, itr_scan_affinity_bf16: the same TMA + tcgen05 main loop; its epilogue only copies the raw region-word
+ *   affinities A = V W^T (bf16 inputs, fp32 accumulate) to `affinity[n_tiles][n_img][128][36]` (fp32).
+ * Phase 2, itr_scan_epilogue_f32: the reference's func_attention / cosine / aggregation (Objectives.py:421-476, 10-15,
+ *   355-366) in fp32 on those affinities, one block per (caption, 4 images).  Inputs: cap_row0[c] = packed row of the
+ *   caption's first word (words of a caption are consecutive rows), region_norm[n_img][36] = |v_k|,
+ *   region_gram[n_img][36][36] (t2i) or the packed word Grams from itr_scan_caption_gram_f32 (i2t; gram_off[c] =
+ *   sum_{c' < c} len_c'^2).  cap_ids[n_ids] selects the captions of this launch (all of length <= max_len); the
+ *   shared-memory tile of a block is sized by max_len, so the caller launches once per length class and chunks over
+ *   images to bound the affinity buffer. */
+int itr_scan_affinity_bf16(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,
+                           float* affinity, void* stream);
+int itr_scan_caption_gram_f32(const uint16_t* words_bf16, const int32_t* cap_row0, const int32_t* cap_lens,
+                              const int64_t* gram_off, int n_cap, int d, float* gram, void* stream);
+int itr_scan_epilogue_f32(const float* affinity, int n_img, const int32_t* cap_row0, const int32_t* cap_lens,
+                          const int32_t* cap_ids, int n_ids, int max_len, const float* row_wnorm, const float* region_norm,
+                          const float* region_gram, const float* cap_gram, const int64_t* gram_off,
+                          int cross_attn, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
+                          float* scores, int64_t ld_scores, void* stream);
+
 /* Debug / bring-up: raw region-word affinities of ONE (word tile, image tile) pair as the
  * tensor cores produced them: out[128 rows][144 cols] fp32. */
 int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,

@@ -165,3 +165,35 @@ def test_tc_equivariance_and_cal_sims_fused_path():
     lo, hi = sharding.shard_bounds(200, 2)[1]
     blk = sharding.sharded_scan_eval(img, cap[lo:hi], lens[lo:hi], lo, 200, cfg(), return_block=True)["sims_block"]
     torch.testing.assert_close(blk, base[:, lo:hi], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["scan_small", "scan_long"])
+@pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
+def test_tc_generic_two_phase_golden(case, direction, lam_sm):
+    """tcgen05 affinities + fp32 epilogue kernel: both directions, all five norm modes, all four aggregations."""
+    g = load_golden(case)
+    img = torch.from_numpy(bits_to_f32(g["img_bits"])).cuda()
+    cap = torch.from_numpy(bits_to_f32(g["cap_bits"])).cuda()
+    lens = g["lens"]
+    for norm in so.RAW_FEATURE_NORMS:
+        for agg in so.AGG_FUNCS:
+            got = ops.scan_scores_tc_generic(img, cap, lens, direction, norm, agg, lam_sm, 6.0).cpu().numpy()
+            want = g["{}|{}|{}|f64".format(direction, norm, agg)]
+            np.testing.assert_allclose(got, want, rtol=RTOL_TC, atol=ATOL_TC, err_msg="{} {} {}".format(direction, norm, agg))
+    # the public entry points dispatch here for i2t (bf16 mode is the default)
+    fn = ob.xattn_score_i2t if direction == "i2t" else ob.xattn_score_t2i
+    got = fn(img, cap, lens, cfg(cross_attn=direction, raw_feature_norm="softmax", agg_func="Mean", lambda_softmax=lam_sm)).cpu().numpy()
+    np.testing.assert_allclose(got, g["{}|softmax|Mean|f64".format(direction)], rtol=RTOL_TC, atol=ATOL_TC)
+
+
+def test_tc_generic_i2t_medium_chunked_vs_fp32_kernel():
+    """Config-4 style block (i2t, Mean, lambda 4): chunked image loop == one chunk == fp32 CUDA-core kernel (1e-3)."""
+    img, cap, lens = itr_b200.synth.scan_inputs(300, 400, 10.5, 14, device="cuda", round_to="bf16")
+    a = ops.scan_scores_tc_generic(img, cap, lens, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+    b = ops.scan_scores_tc_generic(img, cap, lens, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0, max_affinity_bytes=64 << 20)
+    assert torch.equal(a, b)
+    f32 = ops.scan_scores_f32(img, cap, lens, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+    rel = ((a - f32).abs() / f32.abs().clamp_min(1e-6)).max().item()
+    assert rel < 1e-3, rel
+    want = so.scan_scores(img[:16].cpu().numpy(), cap[:24].cpu().numpy(), lens[:24], "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+    np.testing.assert_allclose(a[:16, :24].cpu().numpy(), want, rtol=RTOL_TC, atol=ATOL_TC)
