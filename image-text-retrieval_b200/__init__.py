@@ -17,12 +17,12 @@ from . import synth                                            # noqa: F401
 from . import ops                                              # noqa: F401
 from .objectives import (ContrastiveLoss, TripletLoss, cosine_sim, cosine_similarity, func_attention,   # noqa: F401
                          order_sim, xattn_score_i2t, xattn_score_t2i)
-from .evaluation import cal_recall, cal_sims, cal_sims_and_recall, device_ranks, device_sims, i2t, t2i    # noqa: F401
+from .evaluation import cal_recall, cal_sims, cal_sims_and_recall, device_ranks, device_sims, encode_data, i2t, t2i    # noqa: F401
 from . import sharding                                         # noqa: F401
 
 OBJECTIVES_SYMBOLS = ("cosine_sim", "cosine_similarity", "xattn_score_t2i", "xattn_score_i2t", "func_attention",
                       "ContrastiveLoss", "TripletLoss")
-EVALUATION_SYMBOLS = ("cal_sims", "i2t", "t2i", "cal_recall", "cal_sims_and_recall")
+EVALUATION_SYMBOLS = ("encode_data", "cal_sims", "i2t", "t2i", "cal_recall", "cal_sims_and_recall")
 
 
 def install(objectives_module=None, evaluation_module=None):

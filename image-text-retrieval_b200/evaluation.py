@@ -110,6 +110,63 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
         return out
 
 
+class _ValLogger(dict):
+    """Stand-in for the reference's LogCollector (evaluation.py:43-72) when that class is not importable."""
+
+    def update(self, k, v, n=0):
+        self[k] = v
+
+    def tb_log(self, *a, **k):
+        pass
+
+
+def encode_data(model, data_loader, islength=False):
+    """evaluation.py:75-121 with the device->host hand-off changed: embeddings are
+    collected in PINNED host buffers and returned as numpy views of them, so every caller keeps working
+    (`img_embs[::5]`, `numpy.array([...])`, slicing into folds) while `cal_sims` can gather just the real words of
+    each caption straight from that memory over PCIe instead of re-uploading the zero-padded array block by block.
+    Captions are always laid out at the dataset's maximum length (fixes the reference's first-batch sizing, defect D8)."""
+    try:
+        from itr.metricmodule.evaluation import LogCollector as _LC     # the reference's own collector, if importable
+        val_logger = _LC()
+    except Exception:
+        val_logger = _ValLogger()
+    model.val_start()
+    pin = torch.cuda.is_available()
+    n = len(data_loader.dataset)
+    max_n_word = 0
+    if islength:
+        for batch in data_loader:
+            max_n_word = max(max_n_word, int(batch[4][0]))
+    img_embs = cap_embs = cap_lens = None
+    for batch_data in data_loader:
+        model.logger = val_logger
+        images, boxes, imgs_wh, captions, lengths, ids, captions_mask, captions_type_ids = batch_data
+        with torch.no_grad():
+            emd = model.forward_emb(images=images, boxes=boxes, imgs_wh=imgs_wh, captions=captions, lengths=lengths,
+                                    ids=ids, captions_mask=captions_mask, captions_type_ids=captions_type_ids)
+        img_emb, cap_emb = emd[0].detach().float(), emd[1].detach().float()
+        if img_embs is None:
+            cap_size = [n] + list(cap_emb.shape[1:])
+            if islength:
+                cap_size[1] = max_n_word
+            img_embs = torch.zeros([n] + list(img_emb.shape[1:]), dtype=torch.float32, pin_memory=pin)
+            cap_embs = torch.zeros(cap_size, dtype=torch.float32, pin_memory=pin)
+            cap_lens = np.zeros(n, dtype=np.int32)
+        if cap_emb.dim() == 3 and cap_emb.size(1) > cap_embs.size(1):          # a later, longer batch (defect D8)
+            grown = torch.zeros([n, cap_emb.size(1)] + list(cap_embs.shape[2:]), dtype=torch.float32, pin_memory=pin)
+            grown[:, : cap_embs.size(1)] = cap_embs
+            cap_embs = grown
+        idx = torch.as_tensor(np.asarray(ids), dtype=torch.long)
+        img_embs[idx] = img_emb.cpu()
+        if cap_emb.dim() == 3:
+            cap_embs[idx, : cap_emb.size(1)] = cap_emb.cpu()
+        else:
+            cap_embs[idx] = cap_emb.cpu()
+        cap_lens[np.asarray(ids)] = np.asarray(lengths)
+    return img_embs.numpy(), cap_embs.numpy(), cap_lens
+
+
 def cal_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False):
     """evaluation.py:124-153: host numpy in, host float64 (n_img, n_cap) out."""
     t0 = time.time()

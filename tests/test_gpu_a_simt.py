@@ -196,3 +196,54 @@ def test_cal_sims_dropin_vse_and_scan_fp32():
     lens_d1 = np.minimum(lens[np.arange(60) % 25], cap.size(1))
     want_d1 = so.scan_scores(img.numpy(), cap.numpy(), lens_d1, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
     np.testing.assert_allclose(compat, want_d1, rtol=RTOL32, atol=ATOL32)
+
+
+def test_encode_data_pinned_handoff_and_validate_step_flow():
+    """encode_data drop-in: pinned numpy views out, the reference's own validate_step post-processing
+    (utils.py:152-167: list-comprehension dedupe, cal_sims, i2t, t2i) runs on them unchanged."""
+    img, cap, lens = itr_b200.synth.scan_inputs(8, 40, 10.5, 3, round_to="bf16")
+    img5 = img.repeat_interleave(5, dim=0)                       # the loader yields one image copy per caption
+    order = np.argsort(-lens, kind="stable")                      # batches arrive sorted by length, ids scattered
+
+    class DS:
+        def __len__(self):
+            return 40
+
+    class Loader:
+        dataset = DS()
+
+        def __iter__(self):
+            for s in range(0, 40, 16):
+                ids = order[s:s + 16]
+                l = lens[ids]
+                yield (img5[ids].cuda(), None, None, cap[ids][:, : int(l.max())].cuda(), l.tolist(), ids.tolist(), None, None)
+
+    class Model:
+        sim_enc = None
+        config = cfg(itr_b200_precision="bf16")
+        criterion = ob.ContrastiveLoss(config, margin=0.2, measure="cosine", max_violation=True)
+
+        def val_start(self):
+            pass
+
+        def forward_emb(self, images, captions, lengths, **kw):
+            return images, captions, lengths
+
+    m = Model()
+    img_embs, cap_embs, cap_lens = ev.encode_data(m, Loader(), islength=True)
+    assert isinstance(img_embs, np.ndarray) and img_embs.shape == (40, 36, 1024) and cap_embs.shape == (40, int(lens.max()), 1024)
+    assert torch.from_numpy(cap_embs).is_pinned()
+    np.testing.assert_array_equal(cap_lens, lens)
+    np.testing.assert_array_equal(cap_embs, cap.numpy())
+    img_embs = np.array([img_embs[i] for i in range(0, len(img_embs), 5)])      # utils.py:155
+    sims = ev.cal_sims(m, img_embs, cap_embs, lengths=cap_lens, shard_size=100)
+    want = so.scan_scores(img.numpy(), cap.numpy(), lens, "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    np.testing.assert_allclose(sims, want, rtol=1e-3, atol=1e-6)
+    r = ev.i2t(sims); ri = ev.t2i(sims)
+    assert len(r) == 5 and len(ri) == 5
+    # first-batch sizing (islength=False) no longer breaks when a later batch is longer (defect D8)
+    class Rev(Loader):
+        def __iter__(self):
+            return iter(list(Loader.__iter__(self))[::-1])
+    _, cap2, _ = ev.encode_data(m, Rev(), islength=False)
+    np.testing.assert_array_equal(cap2, cap.numpy())

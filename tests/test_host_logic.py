@@ -77,12 +77,12 @@ def test_install_and_uninstall_on_standin_modules():
     E.cal_sims = "orig_cal"; E.i2t = "orig_i2t"; E.encode_data = "keep"
     itr_b200.install(O, E)
     assert O.cosine_sim is ob.cosine_sim and O.ContrastiveLoss is ob.ContrastiveLoss and O.xattn_score_t2i is ob.xattn_score_t2i
-    assert E.cal_sims is ev.cal_sims and E.i2t is ev.i2t and E.cal_recall is ev.cal_recall
-    assert O.pdist == "keep" and E.encode_data == "keep"
+    assert E.cal_sims is ev.cal_sims and E.i2t is ev.i2t and E.cal_recall is ev.cal_recall and E.encode_data is ev.encode_data
+    assert O.pdist == "keep" and E._itr_b200_orig["encode_data"] == "keep"
     itr_b200.install(O, E)       # idempotent: originals are not overwritten by the patched ones
     assert O._itr_b200_orig["cosine_sim"] == "orig_cos"
     itr_b200.uninstall(O, E)
-    assert O.cosine_sim == "orig_cos" and E.cal_sims == "orig_cal" and not hasattr(E, "_itr_b200_orig")
+    assert O.cosine_sim == "orig_cos" and E.cal_sims == "orig_cal" and E.encode_data == "keep" and not hasattr(E, "_itr_b200_orig")
 
 
 def test_synth_shapes_and_length_sums():

@@ -45,3 +45,24 @@ def test_rank_live(ref):
     (r, (ranks, top1)) = E.t2i(sims, return_ranks=True)
     m, a, b = so.rank_t2i(sims)
     np.testing.assert_array_equal(a, ranks); np.testing.assert_array_equal(b, top1); np.testing.assert_allclose(m, r)
+
+
+def test_install_patches_the_real_reference_modules(ref):
+    """install() on the unmodified reference package: every caller-visible binding now resolves to the drop-in,
+    untouched symbols stay, uninstall() restores the originals."""
+    import itr_b200
+    O, E = ref
+    orig = (O.cosine_sim, O.ContrastiveLoss, E.cal_sims, E.encode_data)
+    try:
+        itr_b200.install()
+        from itr.modalmodule import Models            # binds `Objectives` as a module (Models.py:7)
+        assert Models.Objectives.ContrastiveLoss is itr_b200.ContrastiveLoss
+        assert Models.Objectives.xattn_score_t2i is itr_b200.xattn_score_t2i
+        assert E.cal_sims is itr_b200.cal_sims and E.i2t is itr_b200.i2t and E.encode_data is itr_b200.encode_data
+        assert hasattr(O, "pdist_cos") and hasattr(E, "evalrank_single")            # untouched
+        crit = Models.Objectives.ContrastiveLoss(config={"name": "SCAN", "cross_attn": "i2t", "raw_feature_norm": "clipped_l2norm"},
+                                                 margin=0.2, measure="cosine", max_violation=True)
+        assert crit.sim is itr_b200.xattn_score_i2t
+    finally:
+        itr_b200.uninstall()
+    assert (O.cosine_sim, O.ContrastiveLoss, E.cal_sims, E.encode_data) == orig
