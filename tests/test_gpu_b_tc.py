@@ -197,3 +197,29 @@ def test_tc_generic_i2t_medium_chunked_vs_fp32_kernel():
     assert rel < 1e-3, rel
     want = so.scan_scores(img[:16].cpu().numpy(), cap[:24].cpu().numpy(), lens[:24], "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
     np.testing.assert_allclose(a[:16, :24].cpu().numpy(), want, rtol=RTOL_TC, atol=ATOL_TC)
+
+
+@pytest.mark.parametrize("n_img,lens", [(1, [1]), (1, [5, 3]), (3, [2, 40]), (5, [32] * 9), (7, [1] * 130 + [128, 33]),
+                                        (9, list(range(1, 33)) * 5)])
+def test_tc_edge_shapes(n_img, lens):
+    """Degenerate and schedule-stressing shapes: single image / caption / word, exactly full quarters, more single-word
+    captions than one tile holds, many tiles in several bands, a lone long caption."""
+    lens = np.asarray(lens, dtype=np.int32)
+    g = torch.Generator().manual_seed(int(lens.sum()) + n_img)
+    img = torch.nn.functional.normalize(torch.randn(n_img, 36, 1024, generator=g), dim=-1).to(torch.bfloat16).float()
+    cap = torch.zeros(len(lens), int(lens.max()), 1024)
+    for c, n in enumerate(lens):
+        cap[c, :n] = (torch.randn(int(n), 1024, generator=g) / 32 + 0.3 * img[c % n_img, torch.randint(0, 36, (int(n),), generator=g)]).to(torch.bfloat16).float()
+    sel = np.unique(np.linspace(0, len(lens) - 1, 12).astype(int))
+    want = so.scan_scores(img.numpy(), cap[sel].numpy(), lens[sel], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    got = ob.xattn_score_t2i(img.cuda(), cap.cuda(), lens, cfg()).cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got[:, sel], want, rtol=RTOL_TC, atol=ATOL_TC)
+    i2t_cfg = cfg(cross_attn="i2t", agg_func="Mean", lambda_softmax=4.0)
+    if int(lens.max()) > ops.GENERIC_MAX_WORDS:           # documented limit of the two-phase path: loud, not silent
+        with pytest.raises(ValueError):
+            ob.xattn_score_i2t(img.cuda(), cap.cuda(), lens, i2t_cfg)
+        return
+    got_i2t = ob.xattn_score_i2t(img.cuda(), cap.cuda(), lens, i2t_cfg).cpu().numpy()
+    want_i2t = so.scan_scores(img.numpy(), cap[sel].numpy(), lens[sel], "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+    np.testing.assert_allclose(got_i2t[:, sel], want_i2t, rtol=RTOL_TC, atol=ATOL_TC)
