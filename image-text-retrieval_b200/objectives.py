@@ -7,6 +7,8 @@ Precision modes (config key ``itr_b200_precision`` or env ``ITR_B200_PRECISION``
           fused tcgen05 kernel; i2t and the other norm modes run tcgen05 affinities + an fp32 epilogue
           kernel.  Scores within 1e-3 relative of the reference fed the same rounded inputs.
   "fp32"  CUDA-core float32 kernels: every mode / direction, within 1e-5 relative.
+Under autograd (SCAN training) the scores always come from the float32 kernel and the backward is the native
+closed-form kernel chain of csrc/scan_bwd.cu (captions up to 80 words).
 Anything the bf16 kernel does not cover runs in fp32 mode -- on the GPU, never on the CPU.
 """
 from __future__ import annotations
@@ -29,11 +31,28 @@ def _precision(config):
     return mode
 
 
-def _no_grad_inputs(*tensors):
-    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            "itr_b200: the fused SCAN scorer has no backward yet (SURVEY.md section 8(f), row f3); "
-            "call it under torch.no_grad() / on detached embeddings, or train SCAN with the reference scorer")
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+class _ScanScores(torch.autograd.Function):
+    """SCAN scores under autograd (training, Models.py:219-222): float32 forward kernel, and a backward that
+    recomputes the affinity tiles and returns both embedding gradients from native kernels
+    (``itr_scan_backward_f32``) -- nothing but the inputs is kept between the two."""
+
+    @staticmethod
+    def forward(ctx, images, captions, lens, cross_attn, norm, agg, lam_sm, lam_lse):
+        ctx.save_for_backward(images, captions)
+        ctx.args = (lens, cross_attn, norm, agg, lam_sm, lam_lse)
+        return ops.scan_scores_f32(images, captions, lens, cross_attn, norm, agg, lam_sm, lam_lse)
+
+    @staticmethod
+    def backward(ctx, g):
+        images, captions = ctx.saved_tensors
+        lens, cross_attn, norm, agg, lam_sm, lam_lse = ctx.args
+        d_im, d_cap = ops.scan_backward_f32(images, captions, lens, g, cross_attn, norm, agg, lam_sm, lam_lse)
+        return (d_im.to(images.dtype) if ctx.needs_input_grad[0] else None,
+                d_cap.to(captions.dtype) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -76,7 +95,6 @@ def order_sim(im, s, *args):
 
 
 def _scan(images, captions, cap_lens, config, cross_attn):
-    _no_grad_inputs(images, captions)
     norm, agg = config["raw_feature_norm"], config["agg_func"]
     lam_sm = config["lambda_softmax"]
     lam_lse = config.get("lambda_lse", 6.0) if isinstance(config, dict) else config["lambda_lse"]
@@ -85,6 +103,9 @@ def _scan(images, captions, cap_lens, config, cross_attn):
     if norm in ("l1norm", "clipped_l1norm"):
         # the reference raises NameError here (undefined l1norm_d, defect D4)
         raise ValueError("raw_feature_norm {!r} is not implemented by the reference either".format(norm))
+    if _needs_grad(images, captions):
+        ln = ops.lengths_to_numpy(cap_lens, captions.size(0))
+        return _ScanScores.apply(images, captions, ln, cross_attn, norm, agg, float(lam_sm), float(lam_lse))
     images, captions = images.detach(), captions.detach()
     if _precision(config) == "bf16" and ops.tc_shapes(images, captions) and norm in ("clipped_l2norm", "l2norm", "softmax", "clipped", "no_norm"):
         ln = ops.lengths_to_numpy(cap_lens, captions.size(0))

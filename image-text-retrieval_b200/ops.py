@@ -74,6 +74,62 @@ def scan_scores_f32(images, captions, cap_lens, cross_attn, raw_feature_norm, ag
     return out
 
 
+def scan_backward_f32(images, captions, cap_lens, d_scores, cross_attn, raw_feature_norm, agg_func, lambda_softmax,
+                      lambda_lse, max_workspace_bytes=1 << 30):
+    """Gradients of sum(scores * d_scores) w.r.t. images and captions for ``scan_scores_f32`` (the training
+    backward the reference gets from autograd, Models.py:219-222 over Objectives.py:329-476).  Images are
+    processed in chunks so the coefficient workspace stays under ``max_workspace_bytes``."""
+    images, captions = _cuda_f32(images, "images"), _cuda_f32(captions, "captions")
+    d_scores = _cuda_f32(d_scores, "d_scores")
+    n_img, n_reg, d = images.shape
+    n_cap, lmax, d2 = captions.shape
+    if d != d2:
+        raise ValueError("embedding sizes differ: {} vs {}".format(d, d2))
+    if tuple(d_scores.shape) != (n_img, n_cap):
+        raise ValueError("d_scores must be ({}, {}), got {}".format(n_img, n_cap, tuple(d_scores.shape)))
+    ln = lengths_to_numpy(cap_lens, n_cap)
+    if n_cap and (ln.min() < 1 or ln.max() > lmax):
+        raise ValueError("caption lengths must be in [1, {}]".format(lmax))
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    if cross_attn not in ("t2i", "i2t"):
+        raise ValueError("unknown cross_attn: {}".format(cross_attn))
+    cross = capi.T2I if cross_attn == "t2i" else capi.I2T
+    dev = images.device
+    d_images = torch.empty_like(images)
+    d_captions = torch.zeros_like(captions)
+    if n_img == 0 or n_cap == 0:
+        return d_images.zero_(), d_captions
+    l64 = ln.astype(np.int64)
+    cap_off = np.concatenate([[0], np.cumsum(l64)[:-1]]).astype(np.int32)
+    gram_off = np.concatenate([[0], np.cumsum(l64 * l64)[:-1]]).astype(np.int64)
+    n_words, sum_sq = int(l64.sum()), int((l64 * l64).sum())
+    word_row = (np.repeat(np.arange(n_cap, dtype=np.int64) * lmax - cap_off, ln) + np.arange(n_words)).astype(np.int32)
+    lens_dev = torch.from_numpy(ln).to(dev)
+    cap_off_d, gram_off_d, word_row_d = (torch.from_numpy(a).to(dev) for a in (cap_off, gram_off, word_row))
+    L = capi.lib()
+    chunk = n_img
+    while chunk > 4 and L.itr_scan_backward_workspace_f32(chunk, n_reg, n_cap, n_words, sum_sq, cross) > max_workspace_bytes:
+        chunk = max(4, (chunk // 2 + 3) // 4 * 4)
+    ws_bytes = L.itr_scan_backward_workspace_f32(chunk, n_reg, n_cap, n_words, sum_sq, cross)
+    if ws_bytes < 0:
+        raise ValueError("itr_scan_backward_workspace_f32: bad shape")
+    with torch.cuda.device(dev):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        gram = None
+        if cross_attn == "t2i":
+            gram = torch.empty(n_img, n_reg, n_reg, device=dev, dtype=torch.float32)
+            check(L.itr_region_gram_f32(ptr(images), n_img, n_reg, d, ptr(gram), stream_ptr()))
+        for i0 in range(0, n_img, chunk):
+            i1 = min(i0 + chunk, n_img)
+            ds = d_scores[i0:i1]
+            check(L.itr_scan_backward_f32(ptr(images[i0:i1]), ptr(gram[i0:i1]) if gram is not None else None, ptr(captions),
+                                          ptr(lens_dev), ptr(cap_off_d), ptr(gram_off_d), ptr(word_row_d),
+                                          i1 - i0, n_reg, n_cap, lmax, d, n_words, sum_sq, cross, norm, agg,
+                                          float(lambda_softmax), float(lambda_lse), ptr(ds), ds.stride(0),
+                                          ptr(d_images[i0:i1]), ptr(d_captions), ptr(ws), ws_bytes, stream_ptr()))
+    return d_images, d_captions
+
+
 # ------------------------------------------------------------------------------ SCAN t2i, tensor cores
 @dataclass
 class PreparedImages:

@@ -12,6 +12,9 @@ reference's own functions on them:
   Objectives.cosine_sim                           (:18-21)
   Objectives.TripletLoss (+ torch autograd)       (:482-517; CPU-safe twin of ContrastiveLoss, defect D2)
   evaluation.i2t / t2i                            (itr/metricmodule/evaluation.py:156-222)
+  torch autograd through xattn_score_* (+ TripletLoss)   -> scan_grad.npz, the pin of the training backward
+
+    python oracle/make_golden.py --only scan_grad        regenerates that file alone
 """
 from __future__ import annotations
 
@@ -69,14 +72,70 @@ def scan_case(O, name, n_img, lens, seed, d=1024, r=36):
     print(name, {k: v.shape for k, v in out.items() if "|" not in k})
 
 
+GRAD_FULL = (("clipped_l2norm", "LogSumExp"), ("l2norm", "Mean"), ("softmax", "Max"), ("clipped", "Sum"), ("no_norm", "LogSumExp"))
+
+
+def scan_grad_case(O, name="scan_grad", n=6, lens=(9, 3, 14, 6, 11, 2), seed=105, d=128, r=36, n_probe=4):
+    """Gradients of the reference's own SCAN scorers under torch autograd (float64).  Every mode combination is
+    pinned through ``n_probe`` random projections of both gradients; five combinations per direction and the
+    hinge-loss cases keep the full gradients (stored as float32)."""
+    g = torch.Generator().manual_seed(seed)
+    lens = np.asarray(lens, dtype=np.int32)
+    lmax = int(lens.max())
+    images = torch.nn.functional.normalize(torch.randn(n, r, d, generator=g), dim=-1)
+    caps = torch.zeros(len(lens), lmax, d)
+    for c in range(len(lens)):
+        pick = torch.randint(0, r, (int(lens[c]),), generator=g)
+        w = torch.nn.functional.normalize(images[c % n, pick] + 1.2 / d ** 0.5 * torch.randn(int(lens[c]), d, generator=g), dim=-1)
+        caps[c, :lens[c]] = (0.5 + 1.5 * torch.rand(int(lens[c]), 1, generator=g)) * w
+    img_bits, cap_bits = bf16_bits(images), bf16_bits(caps)
+    images, caps = from_bits(img_bits).double(), from_bits(cap_bits).double()
+    d_scores = torch.randn(n, len(lens), generator=g, dtype=torch.float64)
+    probe_im = torch.randn(n_probe, *images.shape, generator=g, dtype=torch.float64)
+    probe_cap = torch.randn(n_probe, *caps.shape, generator=g, dtype=torch.float64)
+    out = {"img_bits": img_bits, "cap_bits": cap_bits, "lens": lens, "d_scores": d_scores.numpy(),
+           "probe_im": probe_im.float().numpy(), "probe_cap": probe_cap.float().numpy()}
+    probe_im, probe_cap = probe_im.float().double(), probe_cap.float().double()      # what the test will read back
+    for direction, fn, lam_sm in (("t2i", O.xattn_score_t2i, 9.0), ("i2t", O.xattn_score_i2t, 4.0)):
+        for norm in NORMS:
+            for agg in AGGS:
+                cfg = dict(raw_feature_norm=norm, agg_func=agg, lambda_lse=6.0, lambda_softmax=lam_sm)
+                a, b = images.clone().requires_grad_(True), caps.clone().requires_grad_(True)
+                (fn(a, b, lens.tolist(), cfg) * d_scores).sum().backward()
+                key = "{}|{}|{}".format(direction, norm, agg)
+                out[key + "|proj_im"] = (probe_im * a.grad).flatten(1).sum(1).numpy()
+                out[key + "|proj_cap"] = (probe_cap * b.grad).flatten(1).sum(1).numpy()
+                if (norm, agg) in GRAD_FULL:
+                    out[key + "|d_im"] = a.grad.float().numpy()
+                    out[key + "|d_cap"] = b.grad.float().numpy()
+        for mv in (False, True):
+            cfg = dict(raw_feature_norm="clipped_l2norm", agg_func="LogSumExp", lambda_lse=6.0, lambda_softmax=lam_sm)
+            a, b = images.clone().requires_grad_(True), caps.clone().requires_grad_(True)
+            loss = O.TripletLoss(margin=0.2, max_violation=mv)(fn(a, b, lens.tolist(), cfg))
+            loss.backward()
+            key = "{}|hinge|mv{}".format(direction, int(mv))
+            out[key + "|loss"] = np.float64(loss.item())
+            out[key + "|d_im"] = a.grad.float().numpy()
+            out[key + "|d_cap"] = b.grad.float().numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, len(out), "arrays")
+
+
 def main():
     O, E = ref_loader.load()
     torch.set_num_threads(8)
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
+    if "--only" in sys.argv:
+        only = sys.argv[sys.argv.index("--only") + 1]
+        if only != "scan_grad":
+            raise SystemExit("--only supports: scan_grad")
+        scan_grad_case(O)
+        return
 
     scan_case(O, "scan_small", n_img=8, lens=[16, 3, 12, 9, 5, 14, 7, 11, 16, 4, 13, 8], seed=101)
     scan_case(O, "scan_long", n_img=5, lens=[72, 40, 33], seed=102)
+    scan_grad_case(O)
 
     # cosine + hinge
     g = torch.Generator().manual_seed(103)

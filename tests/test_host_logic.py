@@ -53,7 +53,7 @@ def test_scan_config_errors_raise_valueerror_before_any_launch():
         ob.xattn_score_i2t(im, cap, [4, 4], cfg(raw_feature_norm="l1norm"))
     with pytest.raises(ValueError):
         ob._precision(cfg(itr_b200_precision="fp8"))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):          # the autograd path is native too
         ob.xattn_score_t2i(im.requires_grad_(), cap, [4, 4], cfg())
 
 

@@ -86,3 +86,50 @@ def test_ranking():
     np.testing.assert_array_equal(pr, ranks); np.testing.assert_array_equal(pt, top1)
     pr, pt = ref_port.t2i_ranks(sims)
     np.testing.assert_array_equal(pr, ranks_i); np.testing.assert_array_equal(pt, top1_i)
+
+
+# ----------------------------------------------------------------------------- training backward (row f3)
+GRAD_FULL = (("clipped_l2norm", "LogSumExp"), ("l2norm", "Mean"), ("softmax", "Max"), ("clipped", "Sum"), ("no_norm", "LogSumExp"))
+
+
+def _grad_inputs(g):
+    return (bits_to_f32(g["img_bits"]).astype(np.float64), bits_to_f32(g["cap_bits"]).astype(np.float64), g["lens"],
+            g["d_scores"], g["probe_im"].astype(np.float64), g["probe_cap"].astype(np.float64))
+
+
+@pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
+def test_gradient_oracles_match_reference_autograd(direction, lam_sm):
+    """Both gradient restatements (autograd through the port, and the closed form the CUDA kernels implement)
+    against gradients the reference's own xattn_score_* produced under torch autograd in float64."""
+    from oracle import scan_backward as sb
+    g = load_golden("scan_grad")
+    img, cap, lens, ds, p_im, p_cap = _grad_inputs(g)
+    for norm in NORMS:
+        for agg in AGGS:
+            key = "{}|{}|{}".format(direction, norm, agg)
+            for fn in (sb.autograd_grads, sb.coefficient_form):
+                _, d_im, d_cap = fn(img, cap, lens, ds, direction, norm, agg, lam_sm, 6.0)
+                scale_i, scale_c = np.abs(g[key + "|proj_im"]).max(), np.abs(g[key + "|proj_cap"]).max()
+                np.testing.assert_allclose((p_im * d_im).reshape(len(p_im), -1).sum(1), g[key + "|proj_im"], rtol=1e-9,
+                                           atol=1e-10 * scale_i, err_msg=key + " " + fn.__name__)
+                np.testing.assert_allclose((p_cap * d_cap).reshape(len(p_cap), -1).sum(1), g[key + "|proj_cap"], rtol=1e-9,
+                                           atol=1e-10 * scale_c, err_msg=key + " " + fn.__name__)
+                if (norm, agg) in GRAD_FULL:      # stored as float32
+                    np.testing.assert_allclose(d_im, g[key + "|d_im"], rtol=1e-6, atol=1e-7 * np.abs(d_im).max())
+                    np.testing.assert_allclose(d_cap, g[key + "|d_cap"], rtol=1e-6, atol=1e-7 * np.abs(d_cap).max())
+
+
+@pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
+@pytest.mark.parametrize("mv", [False, True])
+def test_scan_hinge_gradient_oracle(direction, lam_sm, mv):
+    """TripletLoss over the SCAN scores, back-propagated to the embeddings (Models.py:219-222)."""
+    from oracle import scan_backward as sb
+    g = load_golden("scan_grad")
+    img, cap, lens = _grad_inputs(g)[:3]
+    scores = so.scan_scores(img, cap, lens, direction, "clipped_l2norm", "LogSumExp", lam_sm, 6.0)
+    loss, d_scores = so.hinge_loss(scores, 0.2, mv)
+    key = "{}|hinge|mv{}".format(direction, int(mv))
+    np.testing.assert_allclose(loss, g[key + "|loss"], rtol=1e-11)
+    _, d_im, d_cap = sb.coefficient_form(img, cap, lens, d_scores, direction, "clipped_l2norm", "LogSumExp", lam_sm, 6.0)
+    np.testing.assert_allclose(d_im, g[key + "|d_im"], rtol=1e-6, atol=1e-7 * np.abs(d_im).max())
+    np.testing.assert_allclose(d_cap, g[key + "|d_cap"], rtol=1e-6, atol=1e-7 * np.abs(d_cap).max())
