@@ -56,8 +56,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-img", type=int, default=5000, help="override for debugging only (invalidates the number)")
     ap.add_argument("--n-cap", type=int, default=25000)
-    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5],
-                    help="BASELINE.json config to measure; 5 (default) is the headline the driver runs")
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5, 6],
+                    help="BASELINE.json config to measure; 5 (default) is the headline the driver runs; "
+                         "6 = SCAN training step (fwd + bwd, batch 128), not a BASELINE config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-caps", type=int, default=300)
     return ap.parse_args()
@@ -235,6 +236,27 @@ def run_side_config(args):
         cpu = (time.perf_counter() - t0) / 50
         out.update(workload="VSE++ ContrastiveLoss max_violation fwd+bwd, batch 128 x 1024", us_per_call=us_ours,
                    us_per_call_eager_pytorch_same_gpu=us_eager, us_per_call_cpu_port=cpu * 1e6)
+    elif args.config == 6:    # SCAN ContrastiveLoss t2i, max_violation, batch 128, embed 1024, fwd + bwd (row f3)
+        lens_np = np.clip(synth.caption_lengths(128, 10.5, 16), 1, 60)
+        img, cap, ln = synth.scan_inputs(128, 128, 10.5, 16, device=dev, lengths=lens_np)
+        a, b = img.clone().requires_grad_(True), cap.clone().requires_grad_(True)
+        cfg = dict(CONFIG, cross_attn="t2i", agg_func="LogSumExp", lambda_softmax=9.0)
+        crit = ob.ContrastiveLoss(cfg, margin=0.2, measure="cosine", max_violation=True)
+        lens_list = [int(x) for x in ln]
+        def ours():
+            a.grad = None; b.grad = None
+            crit(a, b, lens_list).backward()
+        def eager(x=a, y=b):  # the reference's per-caption op sequence under autograd, on the same GPU / on the CPU
+            x.grad = None; y.grad = None
+            ref_port.hinge_any(ref_port.scan_scores.__wrapped__(x, y, lens_list, "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0),
+                               0.2, True).backward()
+        ms_ours, ms_eager = _time_cuda(ours, 30), _time_cuda(eager, 5, warmup=1)
+        ac, bc = img.cpu().clone().requires_grad_(True), cap.cpu().clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        eager(ac, bc)
+        cpu = time.perf_counter() - t0
+        out.update(workload="SCAN t2i ContrastiveLoss max_violation fwd+bwd, batch 128 x 128, 36 regions, embed 1024 (fp32 kernels)",
+                   ms_per_step=ms_ours, ms_per_step_eager_pytorch_same_gpu=ms_eager, ms_per_step_cpu_port=cpu * 1e3)
     else:                     # SCAN 1000 x 5000 blocks
         if args.config == 3:
             shapes = [dict(synth.F30K_SHAPE)]

@@ -292,6 +292,29 @@ scan_bwd_coeff_kernel(ScanBwdParams p) {
   }
 }
 
+// cap_off / gram_off (exclusive prefix sums of len and len^2) and word_row (packed word -> padded row) from the
+// caption lengths, one block; n_cap is a training batch, so the serial prefix is a few microseconds.
+__global__ void __launch_bounds__(256)
+caption_index_kernel(const int32_t* __restrict__ cap_lens, int n_cap, int lmax, int32_t* __restrict__ cap_off,
+                     int64_t* __restrict__ gram_off, int32_t* __restrict__ word_row) {
+  if (threadIdx.x == 0) {
+    int32_t o = 0;
+    int64_t g = 0;
+    for (int c = 0; c < n_cap; ++c) {
+      cap_off[c] = o;
+      gram_off[c] = g;
+      const int n = cap_lens[c];
+      o += n;
+      g += (int64_t)n * n;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_cap; c += 256) {
+    const int n = cap_lens[c], o = cap_off[c];
+    for (int j = 0; j < n; ++j) word_row[o + j] = c * lmax + j;
+  }
+}
+
 // out[e] = sum_g in[g * n + e], fixed order.
 __global__ void __launch_bounds__(256)
 leading_sum_kernel(const float* __restrict__ in, int64_t n, int groups, float* __restrict__ out) {
@@ -412,7 +435,7 @@ blockdiag_apply_kernel(BlockDiag p) {
 static int64_t align64(int64_t floats) { return (floats + 63) / 64 * 64; }
 
 struct BwdWorkspace {
-  int64_t m, mt, tpart, tsum, mcpart, mcsum, total;   // offsets in floats
+  int64_t m, mt, tpart, tsum, mcpart, mcsum, cap_off, gram_off, word_row, total;   // offsets in floats (4-byte units)
   int64_t ldm;
   int n_groups;
 };
@@ -436,6 +459,9 @@ static BwdWorkspace bwd_layout(int n_img, int R, int n_cap, int64_t n_words, int
     w.mcpart = o; o += align64((int64_t)w.n_groups * sum_n2);
     w.mcsum = o; o += align64(sum_n2);
   }
+  w.cap_off = o; o += align64(n_cap);
+  w.gram_off = o; o += align64(2 * (int64_t)n_cap);
+  w.word_row = o; o += align64(n_words);
   w.total = o;
   return w;
 }
@@ -451,13 +477,12 @@ extern "C" int64_t itr_scan_backward_workspace_f32(int n_img, int n_regions, int
 }
 
 extern "C" int itr_scan_backward_f32(const float* images, const float* gram, const float* captions,
-                                     const int32_t* cap_lens, const int32_t* cap_off, const int64_t* gram_off,
-                                     const int32_t* word_row, int n_img, int n_regions, int n_cap, int lmax, int d,
+                                     const int32_t* cap_lens, int n_img, int n_regions, int n_cap, int lmax, int d,
                                      int64_t n_words, int64_t sum_len_sq, int cross_attn, int feature_norm, int agg,
                                      float lambda_softmax, float lambda_lse, const float* d_scores, int64_t ld_dscores,
                                      float* d_images, float* d_captions, void* workspace, int64_t workspace_bytes,
                                      void* stream) {
-  ITR_REQUIRE(images && captions && cap_lens && cap_off && word_row && d_scores && d_images && d_captions && workspace,
+  ITR_REQUIRE(images && captions && cap_lens && d_scores && d_images && d_captions && workspace,
               "itr_scan_backward_f32: null pointer");
   ITR_REQUIRE(cross_attn == ITR_T2I || cross_attn == ITR_I2T, "unknown cross_attn: %d", cross_attn);
   ITR_REQUIRE(feature_norm >= 0 && feature_norm <= ITR_NORM_NONE, "unknown first norm type: %d", feature_norm);
@@ -465,7 +490,6 @@ extern "C" int itr_scan_backward_f32(const float* images, const float* gram, con
   ITR_REQUIRE(n_regions == ITR_REGIONS, "itr_scan_backward_f32: built for %d regions per image, got %d", ITR_REGIONS, n_regions);
   ITR_REQUIRE(lmax >= 1 && lmax <= ITR_MAX_WORDS_F32, "itr_scan_backward_f32: padded caption width %d outside [1, %d]", lmax, ITR_MAX_WORDS_F32);
   ITR_REQUIRE(cross_attn == ITR_I2T || gram != nullptr, "itr_scan_backward_f32: t2i needs the region Gram");
-  ITR_REQUIRE(cross_attn == ITR_T2I || gram_off != nullptr, "itr_scan_backward_f32: i2t needs gram_off");
   ITR_REQUIRE(d > 0 && d % 4 == 0 && ld_dscores >= n_cap, "itr_scan_backward_f32: bad shape (d must be a multiple of 4)");
   ITR_REQUIRE(n_words >= n_cap && n_words <= (int64_t)n_cap * lmax, "itr_scan_backward_f32: n_words inconsistent with n_cap / lmax");
   if (n_img <= 0 || n_cap <= 0) return ITR_OK;
@@ -480,6 +504,11 @@ extern "C" int itr_scan_backward_f32(const float* images, const float* gram, con
   float* ws = static_cast<float*>(workspace);
   const int64_t rows = (int64_t)n_img * R;
   const bool t2i = cross_attn == ITR_T2I;
+  int32_t* cap_off = reinterpret_cast<int32_t*>(ws + w.cap_off);
+  int64_t* gram_off = reinterpret_cast<int64_t*>(ws + w.gram_off);
+  int32_t* word_row = reinterpret_cast<int32_t*>(ws + w.word_row);
+  caption_index_kernel<<<1, 256, 0, st>>>(cap_lens, n_cap, lmax, cap_off, gram_off, word_row);
+  ITR_CHECK_LAUNCH();
 
   ScanBwdParams p;
   p.f = ScanF32Params{images, gram, captions, cap_lens, n_img, R, n_cap, lmax, d, cross_attn, feature_norm, agg,

@@ -597,6 +597,21 @@ rank64_pass_kernel(const double* __restrict__ S, int64_t ld, int n_img, int n_ca
 // =========================================================================================
 using namespace itr;
 
+// The hinge / rank-f64 entry points take their few-KB scratch from the device's default stream-ordered pool.
+// With the default release threshold (0) the pool hands its memory back to the driver at every synchronisation
+// and the next cudaMallocAsync pays for a real allocation; keep up to 64 MB cached instead.
+static void keep_scratch_pool_warm() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = 64ull << 20;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for = dev;
+}
+
 extern "C" const char* itr_last_error(void) { return last_error().c_str(); }
 extern "C" int itr_version(void) { return 100; }
 
@@ -659,6 +674,7 @@ extern "C" int itr_hinge_fwd_bwd_f32(const float* scores, int64_t ld_scores, int
   ITR_REQUIRE(n >= 1 && ld_scores >= n && (dscores == nullptr || ld_dscores >= n), "itr_hinge_fwd_bwd_f32: bad shape");
   cudaStream_t st = as_stream(stream);
   float4* stats = nullptr;
+  keep_scratch_pool_warm();
   ITR_CHECK_CUDA(cudaMallocAsync(&stats, sizeof(float4) * n, st));
   hinge_stats_kernel<<<n, 128, 0, st>>>(scores, ld_scores, n, margin, max_violation, stats);
   int blocks = dscores ? (int)(((int64_t)n * n + 255) / 256) : 1;
@@ -726,6 +742,7 @@ extern "C" int itr_rank_f64(const double* scores, int64_t ld_scores, int n_img, 
   cudaStream_t st = as_stream(stream);
   double *thr_row = nullptr, *thr_col = nullptr;
   unsigned long long *best_row = nullptr, *best_col = nullptr;
+  keep_scratch_pool_warm();
   ITR_CHECK_CUDA(cudaMallocAsync(&thr_row, sizeof(double) * (n_img + n_cap), st));
   thr_col = thr_row + n_img;
   ITR_CHECK_CUDA(cudaMallocAsync(&best_row, sizeof(unsigned long long) * (n_img + n_cap), st));

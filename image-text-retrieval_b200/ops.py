@@ -100,12 +100,8 @@ def scan_backward_f32(images, captions, cap_lens, d_scores, cross_attn, raw_feat
     if n_img == 0 or n_cap == 0:
         return d_images.zero_(), d_captions
     l64 = ln.astype(np.int64)
-    cap_off = np.concatenate([[0], np.cumsum(l64)[:-1]]).astype(np.int32)
-    gram_off = np.concatenate([[0], np.cumsum(l64 * l64)[:-1]]).astype(np.int64)
     n_words, sum_sq = int(l64.sum()), int((l64 * l64).sum())
-    word_row = (np.repeat(np.arange(n_cap, dtype=np.int64) * lmax - cap_off, ln) + np.arange(n_words)).astype(np.int32)
     lens_dev = torch.from_numpy(ln).to(dev)
-    cap_off_d, gram_off_d, word_row_d = (torch.from_numpy(a).to(dev) for a in (cap_off, gram_off, word_row))
     L = capi.lib()
     chunk = n_img
     while chunk > 4 and L.itr_scan_backward_workspace_f32(chunk, n_reg, n_cap, n_words, sum_sq, cross) > max_workspace_bytes:
@@ -123,8 +119,7 @@ def scan_backward_f32(images, captions, cap_lens, d_scores, cross_attn, raw_feat
             i1 = min(i0 + chunk, n_img)
             ds = d_scores[i0:i1]
             check(L.itr_scan_backward_f32(ptr(images[i0:i1]), ptr(gram[i0:i1]) if gram is not None else None, ptr(captions),
-                                          ptr(lens_dev), ptr(cap_off_d), ptr(gram_off_d), ptr(word_row_d),
-                                          i1 - i0, n_reg, n_cap, lmax, d, n_words, sum_sq, cross, norm, agg,
+                                          ptr(lens_dev), i1 - i0, n_reg, n_cap, lmax, d, n_words, sum_sq, cross, norm, agg,
                                           float(lambda_softmax), float(lambda_lse), ptr(ds), ds.stride(0),
                                           ptr(d_images[i0:i1]), ptr(d_captions), ptr(ws), ws_bytes, stream_ptr()))
     return d_images, d_captions

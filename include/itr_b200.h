@@ -81,9 +81,7 @@ int itr_scan_scores_f32(const float* images, const float* gram, const float* cap
  * (Models.py:219-222, Objectives.py:76-115, 329-476): given d_scores = dLoss/dScores (n_img, n_cap) it returns
  * dLoss/dImages and dLoss/dCaptions for the same modes as itr_scan_scores_f32.  The affinity tile is recomputed;
  * nothing is saved by the forward call.
- *   cap_off[c]   first packed word of caption c (exclusive prefix sum of cap_lens), n_words = sum(cap_lens)
- *   gram_off[c]  exclusive prefix sum of cap_lens^2 (ITR_I2T only; may be NULL for ITR_T2I), sum_len_sq its total
- *   word_row[p]  padded row c * lmax + j of packed word p
+ *   n_words      sum(cap_lens);  sum_len_sq = sum(cap_lens^2)  (host-known; they size the workspace)
  *   d_images     (n_img, n_regions, d)  overwritten
  *   d_captions   (n_cap, lmax, d)       ACCUMULATED into (zero it before the first call; lets the caller split
  *                                       the images into chunks); rows of padding words are left untouched
@@ -92,7 +90,6 @@ int itr_scan_scores_f32(const float* images, const float* gram, const float* cap
 int64_t itr_scan_backward_workspace_f32(int n_img, int n_regions, int n_cap, int64_t n_words, int64_t sum_len_sq,
                                         int cross_attn);
 int itr_scan_backward_f32(const float* images, const float* gram, const float* captions, const int32_t* cap_lens,
-                          const int32_t* cap_off, const int64_t* gram_off, const int32_t* word_row,
                           int n_img, int n_regions, int n_cap, int lmax, int d, int64_t n_words, int64_t sum_len_sq,
                           int cross_attn, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                           const float* d_scores, int64_t ld_dscores, float* d_images, float* d_captions,

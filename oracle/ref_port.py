@@ -103,6 +103,19 @@ def hinge(scores, margin=0.0, max_violation=False):
     return cost_s.sum() + cost_im.sum()
 
 
+def hinge_any(scores, margin=0.0, max_violation=False):
+    """``hinge`` for scores on any device (the eye mask follows the scores)."""
+    n = scores.size(0)
+    diag = scores.diag().view(n, 1)
+    eye = torch.eye(n, dtype=torch.bool, device=scores.device)
+    cost_s = (margin + scores - diag.expand_as(scores)).clamp(min=0).masked_fill(eye, 0)
+    cost_im = (margin + scores - diag.t().expand_as(scores)).clamp(min=0).masked_fill(eye, 0)
+    if max_violation:
+        cost_s = cost_s.max(1)[0]
+        cost_im = cost_im.max(0)[0]
+    return cost_s.sum() + cost_im.sum()
+
+
 def i2t_ranks(sims, caps_per_img=5):
     """evaluation.py:156-189, one argsort per image row (numpy, single thread)."""
     n = sims.shape[0]
