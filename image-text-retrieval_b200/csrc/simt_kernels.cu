@@ -162,11 +162,12 @@ struct ScanEpiParams {
 // The reference's epilogue on a block-resident affinity tile (shared by the fp32 kernel and by phase 2 of the
 // tensor-core generic path).  Araw / X: [n_im * R rows][LP] (row = image-major region, column = word), X is scratch.
 // Gctx: t2i -> n_im region Grams (R x R each); i2t -> the caption's word Gram with row stride LP.
-__device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n_im, int n, int img0, int c, int LP,
-                                                   float* Araw, float* X, const float* Gctx, const float* wnorm,
-                                                   const float* vnorm, float* rsim, int RS) {
+template <bool T2I>
+__device__ __forceinline__ void scan_epilogue_dir(const ScanEpiParams& p, int n_im, int n, int img0, int c, int LP,
+                                                  float* Araw, float* X, const float* Gctx, const float* wnorm,
+                                                  const float* vnorm, float* rsim, int RS) {
   const int R = p.R, tid = threadIdx.x, nthr = blockDim.x;
-  const bool t2i = (p.cross_attn == ITR_T2I);
+  constexpr bool t2i = T2I;
   // index helpers: element (image m, source s, query q) of the [row][word] arrays
   const int S = t2i ? R : n, Q = t2i ? n : R;
   auto at = [&](float* base, int m, int s, int q) -> float& {
@@ -220,11 +221,13 @@ __device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n
     }
     const float* G = t2i ? Gctx + m * R * R : Gctx;
     const int gs = t2i ? R : LP;
+    // e^T G e with G symmetric: diagonal once, strict upper triangle twice
     float Qf = 0.f;
     for (int s = 0; s < S; ++s) {
+      const float es = at(X, m, s, q);
       float u = 0.f;
-      for (int s2 = 0; s2 < S; ++s2) u = fmaf(G[s * gs + s2], at(X, m, s2, q), u);
-      Qf = fmaf(at(X, m, s, q), u, Qf);
+      for (int s2 = s + 1; s2 < S; ++s2) u = fmaf(G[s * gs + s2], at(X, m, s2, q), u);
+      Qf = fmaf(es, fmaf(G[s * gs + s], es, 2.f * u), Qf);
     }
     float qn = t2i ? wnorm[q] : vnorm[m * R + q];
     float invZ = 1.f / Z;
@@ -235,8 +238,8 @@ __device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n
   __syncthreads();
 
   // ---- step 4: aggregate over q, one warp per image --------------------------------------
-  const int warp = tid >> 5, lane = tid & 31;
-  if (warp < n_im) {
+  const int lane = tid & 31;
+  for (int warp = tid >> 5; warp < n_im; warp += nthr >> 5) {
     const float* r = rsim + warp * RS;
     float v;
     if (p.agg == ITR_AGG_MAX) {
@@ -252,6 +255,13 @@ __device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n
     }
     if (lane == 0) p.scores[(int64_t)(img0 + warp) * p.ld_scores + c] = v;
   }
+}
+
+__device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n_im, int n, int img0, int c, int LP,
+                                                   float* Araw, float* X, const float* Gctx, const float* wnorm,
+                                                   const float* vnorm, float* rsim, int RS) {
+  if (p.cross_attn == ITR_T2I) scan_epilogue_dir<true>(p, n_im, n, img0, c, LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
+  else scan_epilogue_dir<false>(p, n_im, n, img0, c, LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
 }
 
 __global__ void __launch_bounds__(256)
@@ -305,6 +315,7 @@ scan_f32_kernel(ScanF32Params p) {
 struct ScanEpiKernelParams {
   const float* affinity; int n_img;            // images in this chunk (= second dimension of the dump)
   const int32_t* cap_row0; const int32_t* cap_lens; const int32_t* cap_ids; int n_ids; int LP;
+  int imgs;                                    // images per block
   const float* row_wnorm;                      // [packed rows]
   const float* region_norm;                    // [n_img][R]
   const float* region_gram;                    // t2i: [n_img][R][R]
@@ -312,31 +323,36 @@ struct ScanEpiKernelParams {
   ScanEpiParams e;
 };
 
-// 256 threads for i2t (4 images x 36 regions = 144 work items in the softmax step), 128 for t2i (4 x n words)
+// i2t: 256 threads and 7 images per block (7 x 36 regions = 252 work items in the softmax step) while the tile fits
+// two blocks per SM, else 4 images; t2i: 128 threads, 4 images (4 x n words).
 __global__ void __launch_bounds__(256)
 scan_epilogue_kernel(ScanEpiKernelParams p) {
   const int EPI_THREADS = blockDim.x;
   extern __shared__ __align__(16) float smem[];
-  const int R = p.e.R, RT = SF_IMGS * R, LP = p.LP;
+  const int R = p.e.R, RT = p.imgs * R, LP = p.LP;
   float* Araw = smem;
   float* X = Araw + RT * LP;
   float* Gctx = X + RT * LP;
-  const int g_floats = max(SF_IMGS * R * R, LP * LP);
+  const int g_floats = (p.e.cross_attn == ITR_T2I) ? p.imgs * R * R : LP * LP;
   float* wnorm = Gctx + g_floats;              // LP
   float* vnorm = wnorm + LP;                   // RT
-  float* rsim = vnorm + RT;                    // SF_IMGS * RS
+  float* rsim = vnorm + RT;                    // imgs * RS
   const int RS = max(R, LP);
   const int c = p.cap_ids ? p.cap_ids[blockIdx.x] : (int)blockIdx.x;
-  const int img0 = blockIdx.y * SF_IMGS, tid = threadIdx.x;
-  const int n_im = min(SF_IMGS, p.n_img - img0);
+  const int img0 = blockIdx.y * p.imgs, tid = threadIdx.x;
+  const int n_im = min(p.imgs, p.n_img - img0);
   const int n = p.cap_lens[c];
   const int row0 = p.cap_row0[c];
   const int tile = row0 / ITR_TILE_WORDS, r_in = row0 % ITR_TILE_WORDS;
   const bool t2i = (p.e.cross_attn == ITR_T2I);
   // affinities: global [tile][img][row][k] (k fastest) -> smem Araw[(m*R + k)*LP + j]
-  for (int e = tid; e < n_im * n * R; e += EPI_THREADS) {
-    int k = e % R, j = (e / R) % n, m = e / (R * n);
-    Araw[(m * R + k) * LP + j] = p.affinity[(((size_t)tile * p.n_img + img0 + m) * ITR_TILE_WORDS + r_in + j) * R + k];
+  for (int m = 0; m < n_im; ++m) {                      // n contiguous rows of R floats per image
+    const float* src = p.affinity + (((size_t)tile * p.n_img + img0 + m) * ITR_TILE_WORDS + r_in) * R;
+    float* dst = Araw + m * R * LP;
+    for (int e = tid; e < n * R; e += EPI_THREADS) {
+      const int j = e / R, k = e - j * R;
+      dst[k * LP + j] = src[e];
+    }
   }
   if (t2i) {
     for (int e = tid; e < n_im * R * R; e += EPI_THREADS) Gctx[e] = p.region_gram[(size_t)img0 * R * R + e];
@@ -788,16 +804,22 @@ extern "C" int itr_scan_epilogue_f32(const float* affinity, int n_img, const int
   ITR_REQUIRE(cross_attn == ITR_I2T ? (cap_gram && gram_off) : (region_gram != nullptr), "itr_scan_epilogue_f32: missing Gram input");
   ITR_REQUIRE(max_len >= 1 && max_len <= ITR_TILE_WORDS && n_ids >= 0, "itr_scan_epilogue_f32: bad shape");
   if (n_img <= 0 || n_ids <= 0) return ITR_OK;
-  const int R = ITR_REGIONS, RT = SF_IMGS * R, LP = max_len + 1;
-  ScanEpiKernelParams p{affinity, n_img, cap_row0, cap_lens, cap_ids, n_ids, LP, row_wnorm, region_norm, region_gram, cap_gram, gram_off,
+  const int R = ITR_REGIONS, LP = (max_len + 1) | 1;      // odd row pitch: the i2t accesses stride by LP across lanes
+  auto smem_for = [&](int imgs) {
+    const int RT = imgs * R;
+    const int g_floats = (cross_attn == ITR_T2I) ? imgs * R * R : LP * LP;
+    const int rs = R > LP ? R : LP;
+    return sizeof(float) * (2 * (size_t)RT * LP + g_floats + LP + RT + (size_t)imgs * rs);
+  };
+  int imgs = SF_IMGS;
+  if (cross_attn == ITR_I2T && smem_for(7) <= 110 * 1024) imgs = 7;
+  const size_t smem = smem_for(imgs);
+  ScanEpiKernelParams p{affinity, n_img, cap_row0, cap_lens, cap_ids, n_ids, LP, imgs, row_wnorm, region_norm, region_gram, cap_gram, gram_off,
                         ScanEpiParams{R, cross_attn, feature_norm, agg, lambda_softmax, lambda_lse, scores, ld_scores}};
-  int g_floats = SF_IMGS * R * R > LP * LP ? SF_IMGS * R * R : LP * LP;
-  int rs = R > LP ? R : LP;
-  size_t smem = sizeof(float) * (2 * (size_t)RT * LP + g_floats + LP + RT + SF_IMGS * rs);
   ITR_REQUIRE(smem <= 227 * 1024, "itr_scan_epilogue_f32: caption of %d words needs %zu bytes of shared memory", max_len, smem);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(n_ids, (n_img + SF_IMGS - 1) / SF_IMGS);
-  ITR_REQUIRE(grid.y <= 65535, "itr_scan_epilogue_f32: more than %d images per call", 65535 * SF_IMGS);
+  dim3 grid(n_ids, (n_img + imgs - 1) / imgs);
+  ITR_REQUIRE(grid.y <= 65535, "itr_scan_epilogue_f32: more than %d images per call", 65535 * imgs);
   scan_epilogue_kernel<<<grid, cross_attn == ITR_I2T ? 256 : 128, smem, as_stream(stream)>>>(p);
   ITR_CHECK_LAUNCH();
   return ITR_OK;
