@@ -728,28 +728,33 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
 
 // ---------------------------------------------------------------------------- prep kernels
 // One warp per packed row: gather the word (or zeros), round to bf16, norm of the rounded row.
-__global__ void __launch_bounds__(256)
+// 128 threads x <= 32 registers per block: exactly the register-file slice the persistent score kernel leaves free
+// (640 threads x 96 registers), so the PCIe gather of the next caption chunk co-resides with a running score kernel
+// instead of queueing behind it (ops.scan_t2i_scores_from_host).
+__global__ void __launch_bounds__(128, 16)
 pack_words_kernel(const float* __restrict__ captions, int lmax, int d, const int4* __restrict__ row_meta, int n_rows,
                   uint16_t* __restrict__ out, float* __restrict__ wnorm) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const int4 meta = row_meta[row];
-  uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * d);
-  float ss = 0.f;
-  if (meta.x < 0) {
-    for (int v = lane; v < d / 4; v += 32) dst[v] = make_uint2(0u, 0u);
-  } else {
-    const float4* src = reinterpret_cast<const float4*>(captions + ((size_t)meta.x * lmax + meta.y) * d);
-    for (int v = lane; v < d / 4; v += 32) {
-      float4 x = src[v];
-      uint16_t b0 = f32_to_bf16_rn(x.x), b1 = f32_to_bf16_rn(x.y), b2 = f32_to_bf16_rn(x.z), b3 = f32_to_bf16_rn(x.w);
-      float r0 = bf16_to_f32(b0), r1 = bf16_to_f32(b1), r2 = bf16_to_f32(b2), r3 = bf16_to_f32(b3);
-      ss = fmaf(r0, r0, ss); ss = fmaf(r1, r1, ss); ss = fmaf(r2, r2, ss); ss = fmaf(r3, r3, ss);
-      dst[v] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 4) {
+    const int4 meta = row_meta[row];
+    uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * d);
+    float ss = 0.f;
+    if (meta.x < 0) {
+      for (int v = lane; v < d / 4; v += 32) dst[v] = make_uint2(0u, 0u);
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(captions + ((size_t)meta.x * lmax + meta.y) * d);
+#pragma unroll 4
+      for (int v = lane; v < d / 4; v += 32) {
+        float4 x = src[v];
+        uint16_t b0 = f32_to_bf16_rn(x.x), b1 = f32_to_bf16_rn(x.y), b2 = f32_to_bf16_rn(x.z), b3 = f32_to_bf16_rn(x.w);
+        float r0 = bf16_to_f32(b0), r1 = bf16_to_f32(b1), r2 = bf16_to_f32(b2), r3 = bf16_to_f32(b3);
+        ss = fmaf(r0, r0, ss); ss = fmaf(r1, r1, ss); ss = fmaf(r2, r2, ss); ss = fmaf(r3, r3, ss);
+        dst[v] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
+      }
     }
+    ss = warp_sum(ss);
+    if (lane == 0) wnorm[row] = sqrtf(ss);
   }
-  ss = warp_sum(ss);
-  if (lane == 0) wnorm[row] = sqrtf(ss);
 }
 
 // One block (192 threads) per image: round the 36 regions to bf16 and build the image's Gram pack (fp16
@@ -943,8 +948,19 @@ extern "C" int itr_scan_pack_words_bf16(const float* captions, int n_cap, int lm
   ITR_REQUIRE(n_cap >= 0 && lmax >= 1 && n_tiles >= 0, "itr_scan_pack_words_bf16: bad shape");
   if (n_tiles == 0) return ITR_OK;
   const int n_rows = n_tiles * BLOCK_M;
-  pack_words_kernel<<<(n_rows + 7) / 8, 256, 0, as_stream(stream)>>>(captions, lmax, d, reinterpret_cast<const int4*>(row_meta),
-                                                                     n_rows, words_bf16, row_wnorm);
+  // Host (pinned) source: the gather is PCIe-bound, so one resident block per SM is plenty -- and one block per SM is
+  // what fits next to a running score CTA whatever the launch order.  Device source: one block per 4 rows (HBM-bound).
+  int grid = (n_rows + 3) / 4;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, captions) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (grid > sms) grid = sms;
+  } else {
+    cudaGetLastError();   // a plain cudaMalloc'ed / unregistered pointer is not an error here
+  }
+  pack_words_kernel<<<grid, 128, 0, as_stream(stream)>>>(captions, lmax, d, reinterpret_cast<const int4*>(row_meta),
+                                                         n_rows, words_bf16, row_wnorm);
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }

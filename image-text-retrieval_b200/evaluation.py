@@ -50,6 +50,15 @@ def _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths):
     return ln
 
 
+def _scan_t2i_from(pi, caps, ln, norm, config, dev):
+    """Fused t2i scores from prepared images and captions that are either on the device or in pinned host memory
+    (gathered in place over PCIe, pipelined against the score kernel)."""
+    args = (norm, config["agg_func"], config["lambda_softmax"], config.get("lambda_lse", 6.0))
+    if not caps.is_cuda:
+        return ops.scan_t2i_scores_from_host(pi, caps, ln, *args, device=dev)
+    return ops.scan_t2i_scores_bf16(pi, ops.prepare_captions(caps, ln, device=dev), *args)
+
+
 def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False,
                 image_group=None):
     """The score matrix as a CUDA float32 tensor (n_img, n_cap); inputs host or device.
@@ -79,9 +88,7 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
                 if not caps.is_cuda and not caps.is_pinned():
                     caps = caps.to(dev)
                 pi = ops.prepare_images_sharded(img_embs, image_group, dev)
-                pc = ops.prepare_captions(caps, ln, device=dev)
-                return ops.scan_t2i_scores_bf16(pi, pc, norm_, config["agg_func"], config["lambda_softmax"],
-                                                config.get("lambda_lse", 6.0))
+                return _scan_t2i_from(pi, caps, ln, norm_, config, dev)
             img = _to_device(img_embs, dev)
             if cal_fun is objectives.cosine_sim:
                 return ops.cosine_scores(img, _to_device(cap_embs, dev))
@@ -95,8 +102,7 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
                 if not caps.is_cuda and not caps.is_pinned():
                     caps = caps.to(dev)          # pageable host memory: one plain copy
                 pi = ops.prepare_images(img)
-                pc = ops.prepare_captions(caps, ln, device=dev)   # pinned host memory is gathered in place
-                return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, config["lambda_softmax"], config.get("lambda_lse", 6.0))
+                return _scan_t2i_from(pi, caps, ln, norm, config, dev)
             return cal_fun(img, _to_device(cap_embs, dev), ln, config)
         # anything else (learned similarity heads, CAMERA): the reference's blocked loop, with sliced lengths
         out = torch.empty(n_img, n_cap, device=dev, dtype=torch.float32)

@@ -258,6 +258,63 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
     return out
 
 
+def host_caption_chunks(lens, fractions=(1.0 / 16, 3.0 / 16, 3.0 / 4), multiple=5, min_words=16384):
+    """[(c0, c1)] caption ranges for the pipelined host path: a small first chunk (its PCIe gather is the only one
+    nobody hides), then growing ones.  Boundaries on multiples of `multiple`; small inputs stay in one piece."""
+    n_cap = len(lens)
+    total = int(np.sum(lens))
+    if n_cap == 0 or total < 4 * min_words:
+        return [(0, n_cap)]
+    csum = np.cumsum(lens)
+    cuts, acc = [], 0.0
+    for f in fractions[:-1]:
+        acc += f
+        c = int(np.searchsorted(csum, acc * total)) + 1
+        c = min(n_cap, (c + multiple - 1) // multiple * multiple)
+        if c > (cuts[-1] if cuts else 0) and c < n_cap:
+            cuts.append(c)
+    edges = [0] + cuts + [n_cap]
+    return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+
+def scan_t2i_scores_from_host(pi: PreparedImages, captions, cap_lens, raw_feature_norm, agg_func, lambda_softmax, lambda_lse,
+                              device=None, chunks=None):
+    """Fused t2i scores for captions living in PINNED host memory: the gather of chunk k+1 over PCIe
+    (itr_scan_pack_words_bf16 on a side stream) runs under the score kernel of chunk k, so only the first, small
+    chunk's transfer is exposed.  Returns the (n_img, n_cap) score matrix on the current stream."""
+    n_cap = captions.size(0)
+    ln = lengths_to_numpy(cap_lens, n_cap)
+    dev = pi.images_bf16.device
+    out = torch.empty(pi.n_img, n_cap, device=dev, dtype=torch.float32)
+    if chunks is None:
+        chunks = host_caption_chunks(ln)
+    if len(chunks) == 1:
+        pc = prepare_captions(captions, ln, device=dev)
+        return scan_t2i_scores_bf16(pi, pc, raw_feature_norm, agg_func, lambda_softmax, lambda_lse, out=out)
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    for c0, c1 in chunks:
+        with torch.cuda.stream(side):
+            pc = prepare_captions(captions[c0:c1], ln[c0:c1], device=dev)
+            ready = side.record_event()
+        main.wait_event(ready)
+        for t in (pc.words_bf16, pc.row_meta, pc.row_wnorm):
+            t.record_stream(main)
+        scan_t2i_scores_bf16(pi, pc, raw_feature_norm, agg_func, lambda_softmax, lambda_lse, out=out[:, c0:c1])
+    return out
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def caption_rows(pc: PreparedCaptions, lengths):
     """cap_row0[c] = packed row index of caption c's first word (a caption's words are consecutive packed rows)."""
     meta = pc.row_meta

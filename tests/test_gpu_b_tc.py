@@ -223,3 +223,21 @@ def test_tc_edge_shapes(n_img, lens):
     got_i2t = ob.xattn_score_i2t(img.cuda(), cap.cuda(), lens, i2t_cfg).cpu().numpy()
     want_i2t = so.scan_scores(img.numpy(), cap[sel].numpy(), lens[sel], "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
     np.testing.assert_allclose(got_i2t[:, sel], want_i2t, rtol=RTOL_TC, atol=ATOL_TC)
+
+
+def test_tc_pipelined_host_captions_match_device_path():
+    """Captions in pinned host memory: chunked PCIe gather on a side stream under the score kernel gives the same
+    matrix as the one-shot device path, bit for bit (same kernel, same packing within a chunk boundary or not)."""
+    rng = np.random.default_rng(5)
+    lens = np.clip(rng.poisson(9, 400) + 1, 1, 30).astype(np.int32)
+    img, cap, ln = itr_b200.synth.scan_inputs(13, 400, 10.5, 21, device="cuda", lengths=lens)
+    pi = ops.prepare_images(img)
+    want = ops.scan_t2i_scores_bf16(pi, ops.prepare_captions(cap, ln), "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    host = cap.cpu().pin_memory()
+    assert ops.host_caption_chunks(ln) == [(0, 400)]
+    chunks = ops.host_caption_chunks(ln, min_words=64)
+    assert len(chunks) == 3 and chunks[0][0] == 0 and chunks[-1][1] == 400 and all(a % 5 == 0 for a, _ in chunks)
+    for ch in (None, chunks, [(0, 5), (5, 395), (395, 400)]):
+        got = ops.scan_t2i_scores_from_host(pi, host, ln, "clipped_l2norm", "LogSumExp", 9.0, 6.0, chunks=ch)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol=1e-7)
