@@ -258,7 +258,7 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
     return out
 
 
-def host_caption_chunks(lens, fractions=(1.0 / 16, 3.0 / 16, 3.0 / 4), multiple=5, min_words=16384):
+def host_caption_chunks(lens, fractions=(1.0 / 16, 3.0 / 16, 3.0 / 4), multiple=5, min_words=2048):
     """[(c0, c1)] caption ranges for the pipelined host path: a small first chunk (its PCIe gather is the only one
     nobody hides), then growing ones.  Boundaries on multiples of `multiple`; small inputs stay in one piece."""
     n_cap = len(lens)
