@@ -15,23 +15,33 @@ __version__ = "0.1.0"
 from . import _capi as capi                                    # noqa: F401  (ctypes binding; loads lazily)
 from . import synth                                            # noqa: F401
 from . import ops                                              # noqa: F401
-from .objectives import (ContrastiveLoss, TripletLoss, cosine_sim, cosine_similarity, func_attention,   # noqa: F401
-                         order_sim, xattn_score_i2t, xattn_score_t2i)
+from .objectives import (ContrastiveLoss, MultiViewMatching, TripletLoss, cosine_sim, cosine_similarity,   # noqa: F401
+                         func_attention, order_sim, xattn_score_i2t, xattn_score_t2i)
 from .evaluation import cal_recall, cal_sims, cal_sims_and_recall, device_ranks, device_sims, encode_data, i2t, t2i    # noqa: F401
 from . import sharding                                         # noqa: F401
 
-OBJECTIVES_SYMBOLS = ("cosine_sim", "cosine_similarity", "xattn_score_t2i", "xattn_score_i2t", "func_attention",
+OBJECTIVES_SYMBOLS = ("cosine_sim", "order_sim", "cosine_similarity", "xattn_score_t2i", "xattn_score_i2t", "func_attention",
                       "ContrastiveLoss", "TripletLoss")
+FUSION_SYMBOLS = ("MultiViewMatching",)
 EVALUATION_SYMBOLS = ("encode_data", "cal_sims", "i2t", "t2i", "cal_recall", "cal_sims_and_recall")
 
 
-def install(objectives_module=None, evaluation_module=None):
+def _fusion_module():
+    """itr.modalmodule.Fusionmodule, or None when it (or one of its own dependencies) cannot be imported."""
+    import importlib
+    try:
+        return importlib.import_module("itr.modalmodule.Fusionmodule")
+    except Exception:          # noqa: BLE001  (optional third patch target; its imports are the reference's business)
+        return None
+
+
+def install(objectives_module=None, evaluation_module=None, fusion_module=None):
     """Monkey-patch the accelerated symbols into the (already importable) reference package.
 
     ``itr/utils.py:11`` binds the evaluation module as ``eval`` and ``itr/modalmodule/Models.py:7``
-    binds ``Objectives`` as a module, so attribute patching is seen by every caller
+    binds ``Objectives`` / ``Fusionmodule`` as modules, so attribute patching is seen by every caller
     (SURVEY.md section 8(b)).  The originals are kept under ``module._itr_b200_orig``.
-    Returns the two patched modules.
+    Returns the patched (Objectives, evaluation) modules.
     """
     import importlib
     from . import evaluation as _ev, objectives as _ob
@@ -39,7 +49,12 @@ def install(objectives_module=None, evaluation_module=None):
         objectives_module = importlib.import_module("itr.modalmodule.Objectives")
     if evaluation_module is None:
         evaluation_module = importlib.import_module("itr.metricmodule.evaluation")
-    for mod, names, src in ((objectives_module, OBJECTIVES_SYMBOLS, _ob), (evaluation_module, EVALUATION_SYMBOLS, _ev)):
+    if fusion_module is None:
+        fusion_module = _fusion_module()
+    targets = [(objectives_module, OBJECTIVES_SYMBOLS, _ob), (evaluation_module, EVALUATION_SYMBOLS, _ev)]
+    if fusion_module is not None:
+        targets.append((fusion_module, FUSION_SYMBOLS, _ob))
+    for mod, names, src in targets:
         saved = getattr(mod, "_itr_b200_orig", None)
         if saved is None:
             saved = {}
@@ -51,13 +66,17 @@ def install(objectives_module=None, evaluation_module=None):
     return objectives_module, evaluation_module
 
 
-def uninstall(objectives_module=None, evaluation_module=None):
+def uninstall(objectives_module=None, evaluation_module=None, fusion_module=None):
     import importlib
     if objectives_module is None:
         objectives_module = importlib.import_module("itr.modalmodule.Objectives")
     if evaluation_module is None:
         evaluation_module = importlib.import_module("itr.metricmodule.evaluation")
-    for mod in (objectives_module, evaluation_module):
+    if fusion_module is None:
+        fusion_module = _fusion_module()
+    for mod in (objectives_module, evaluation_module, fusion_module):
+        if mod is None:
+            continue
         for name, fn in getattr(mod, "_itr_b200_orig", {}).items():
             setattr(mod, name, fn)
         for name in ("cal_sims_and_recall",):

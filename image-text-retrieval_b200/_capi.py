@@ -30,6 +30,10 @@ SIGNATURES = {
     "itr_scan_backward_workspace_f32": (_l, [_i, _i, _i, _l, _l, _i]),
     "itr_scan_backward_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _i, _i, _i, _f, _f,
                                    _p, _l, _p, _p, _p, _l, _p]),
+    "itr_order_scores_f32": (_i, [_p, _p, _i, _i, _i, _p, _l, _p]),
+    "itr_order_backward_f32": (_i, [_p, _p, _p, _l, _p, _l, _i, _i, _i, _p, _p, _p]),
+    "itr_multiview_scores_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _l, _p, _p]),
+    "itr_multiview_backward_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _l, _p, _p, _p, _p, _p]),
     "itr_scan_plan_max_tiles": (_i, [_p, _i]),
     "itr_scan_plan_words": (_i, [_p, _i, _p, C.POINTER(C.c_int)]),
     "itr_scan_pack_words_bf16": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),

@@ -824,3 +824,169 @@ extern "C" int itr_scan_epilogue_f32(const float* affinity, int n_img, const int
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }
+
+// =========================================================================================
+// the two remaining dense similarity measures.
+//   CAMERA MultiViewMatching (Fusionmodule.py:670-692): score[i][c] = max_v  imgs[i][v] . caps[c]
+//   order_sim (Objectives.py:24-30):                    score[i][c] = -|max(s_c - im_i, 0)|_2
+// =========================================================================================
+namespace itr {
+
+// C[(i, v)][c] -> score[i][c] = max_v, arg[i][c] = first v attaining it
+__global__ void __launch_bounds__(256)
+view_max_kernel(const float* __restrict__ C, int n_img, int n_views, int n_cap, float* __restrict__ scores, int64_t ld,
+                int32_t* __restrict__ arg) {
+  const int c = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  if (c >= n_cap) return;
+  const float* src = C + (int64_t)i * n_views * n_cap + c;
+  float best = src[0];
+  int bv = 0;
+  for (int v = 1; v < n_views; ++v) {
+    const float x = src[(int64_t)v * n_cap];
+    if (x > best) { best = x; bv = v; }
+  }
+  scores[(int64_t)i * ld + c] = best;
+  if (arg) arg[(int64_t)i * n_cap + c] = bv;
+}
+
+// E[(i, v)][c] = dS[i][c] if v == arg[i][c] else 0
+__global__ void __launch_bounds__(256)
+view_scatter_kernel(const float* __restrict__ dS, int64_t ld, const int32_t* __restrict__ arg, int n_img, int n_views,
+                    int n_cap, float* __restrict__ E) {
+  const int c = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  if (c >= n_cap) return;
+  const float g = dS[(int64_t)i * ld + c];
+  const int a = arg[(int64_t)i * n_cap + c];
+  for (int v = 0; v < n_views; ++v) E[((int64_t)i * n_views + v) * n_cap + c] = (v == a) ? g : 0.f;
+}
+
+// order_sim forward: 32 x 32 scores per block, 2 x 2 per thread, K swept through shared memory in slabs of 32.
+__global__ void __launch_bounds__(256)
+order_scores_kernel(const float* __restrict__ im, const float* __restrict__ s, int n_img, int n_cap, int d,
+                    float* __restrict__ scores, int64_t ld) {
+  __shared__ float Is[32][33], Ss[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  float acc[2][2] = {};
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int r = e >> 5, k = e & 31;
+      Is[r][k] = (i0 + r < n_img && k0 + k < d) ? im[(int64_t)(i0 + r) * d + k0 + k] : 0.f;
+      Ss[r][k] = (c0 + r < n_cap && k0 + k < d) ? s[(int64_t)(c0 + r) * d + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = Is[ty * 2][k], a1 = Is[ty * 2 + 1][k], b0 = Ss[tx * 2][k], b1 = Ss[tx * 2 + 1][k];
+      float y;
+      y = fmaxf(b0 - a0, 0.f); acc[0][0] = fmaf(y, y, acc[0][0]);
+      y = fmaxf(b1 - a0, 0.f); acc[0][1] = fmaf(y, y, acc[0][1]);
+      y = fmaxf(b0 - a1, 0.f); acc[1][0] = fmaf(y, y, acc[1][0]);
+      y = fmaxf(b1 - a1, 0.f); acc[1][1] = fmaf(y, y, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int i = i0 + ty * 2 + a, c = c0 + tx * 2 + b;
+      if (i < n_img && c < n_cap) scores[(int64_t)i * ld + c] = -sqrtf(acc[a][b]);
+    }
+}
+
+// order_sim backward.  With y = max(s_c - im_i, 0), N = |y| = -score and w = dS / N (0 where N = 0):
+//   d_im[i] = +sum_c w[i][c] y        d_s[c] = -sum_i w[i][c] y
+// ROWS_ARE_IMAGES: block (row i, 256-wide slab of d) loops over all captions; otherwise block (row c) loops over images.
+template <bool ROWS_ARE_IMAGES>
+__global__ void __launch_bounds__(256)
+order_backward_kernel(const float* __restrict__ im, const float* __restrict__ s, const float* __restrict__ scores, int64_t ld_s,
+                      const float* __restrict__ dS, int64_t ld_ds, int n_img, int n_cap, int d, float* __restrict__ out) {
+  const int row = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+  const int n_other = ROWS_ARE_IMAGES ? n_cap : n_img;
+  __shared__ float w[256];
+  const float mine = (k < d) ? (ROWS_ARE_IMAGES ? im : s)[(int64_t)row * d + k] : 0.f;
+  float acc = 0.f;
+  for (int o0 = 0; o0 < n_other; o0 += 256) {
+    const int o = o0 + threadIdx.x;
+    float wv = 0.f;
+    if (o < n_other) {
+      const int i = ROWS_ARE_IMAGES ? row : o, c = ROWS_ARE_IMAGES ? o : row;
+      const float nrm = -scores[(int64_t)i * ld_s + c];
+      wv = nrm > 0.f ? dS[(int64_t)i * ld_ds + c] / nrm : 0.f;
+    }
+    __syncthreads();
+    w[threadIdx.x] = wv;
+    __syncthreads();
+    if (k < d) {
+      const int lim = min(256, n_other - o0);
+      const float* other = (ROWS_ARE_IMAGES ? s : im) + (int64_t)o0 * d + k;
+      for (int j = 0; j < lim; ++j) {
+        const float x = other[(int64_t)j * d];
+        const float y = ROWS_ARE_IMAGES ? fmaxf(x - mine, 0.f) : fmaxf(mine - x, 0.f);
+        acc = fmaf(w[j], y, acc);
+      }
+    }
+  }
+  if (k < d) out[(int64_t)row * d + k] = ROWS_ARE_IMAGES ? acc : -acc;
+}
+
+}  // namespace itr
+
+extern "C" int itr_multiview_scores_f32(const float* imgs, const float* caps, int n_img, int n_views, int n_cap, int d,
+                                        float* workspace, float* scores, int64_t ld_scores, int32_t* argmax, void* stream) {
+  ITR_REQUIRE(imgs && caps && workspace && scores, "itr_multiview_scores_f32: null pointer");
+  ITR_REQUIRE(n_img >= 0 && n_cap >= 0 && n_views >= 1 && d > 0 && ld_scores >= n_cap, "itr_multiview_scores_f32: bad shape");
+  ITR_REQUIRE((int64_t)n_img * n_views < (1ll << 31) && n_img <= 65535, "itr_multiview_scores_f32: too many image views per call");
+  if (n_img == 0 || n_cap == 0) return ITR_OK;
+  cudaStream_t st = as_stream(stream);
+  int rc = launch_sgemm(imgs, d, 1, caps, d, 1, workspace, n_cap, n_img * n_views, n_cap, d, st);
+  if (rc) return rc;
+  view_max_kernel<<<dim3((n_cap + 255) / 256, n_img), 256, 0, st>>>(workspace, n_img, n_views, n_cap, scores, ld_scores, argmax);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_multiview_backward_f32(const float* imgs, const float* caps, int n_img, int n_views, int n_cap, int d,
+                                          const float* d_scores, int64_t ld_dscores, const int32_t* argmax, float* workspace,
+                                          float* d_imgs, float* d_caps, void* stream) {
+  ITR_REQUIRE(imgs && caps && d_scores && argmax && workspace, "itr_multiview_backward_f32: null pointer");
+  ITR_REQUIRE(n_img >= 0 && n_cap >= 0 && n_views >= 1 && d > 0 && ld_dscores >= n_cap, "itr_multiview_backward_f32: bad shape");
+  ITR_REQUIRE((int64_t)n_img * n_views < (1ll << 31) && n_img <= 65535, "itr_multiview_backward_f32: too many image views per call");
+  if (n_img == 0 || n_cap == 0) return ITR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int rows = n_img * n_views;
+  view_scatter_kernel<<<dim3((n_cap + 255) / 256, n_img), 256, 0, st>>>(d_scores, ld_dscores, argmax, n_img, n_views, n_cap, workspace);
+  ITR_CHECK_LAUNCH();
+  int rc = ITR_OK;
+  // d_imgs[(i,v)][k] = sum_c E[(i,v)][c] caps[c][k];   d_caps[c][k] = sum_(i,v) E[(i,v)][c] imgs[(i,v)][k]
+  if (d_imgs) { rc = launch_sgemm(workspace, n_cap, 1, caps, 1, d, d_imgs, d, rows, d, n_cap, st); if (rc) return rc; }
+  if (d_caps) { rc = launch_sgemm(workspace, 1, n_cap, imgs, 1, d, d_caps, d, n_cap, d, rows, st); if (rc) return rc; }
+  return ITR_OK;
+}
+
+extern "C" int itr_order_scores_f32(const float* im, const float* s, int n_img, int n_cap, int d, float* scores,
+                                    int64_t ld_scores, void* stream) {
+  ITR_REQUIRE(im && s && scores, "itr_order_scores_f32: null pointer");
+  ITR_REQUIRE(n_img >= 0 && n_cap >= 0 && d > 0 && ld_scores >= n_cap, "itr_order_scores_f32: bad shape");
+  if (n_img == 0 || n_cap == 0) return ITR_OK;
+  dim3 grid((n_cap + 31) / 32, (n_img + 31) / 32);
+  ITR_REQUIRE(grid.y <= 65535, "itr_order_scores_f32: too many images per call");
+  order_scores_kernel<<<grid, 256, 0, as_stream(stream)>>>(im, s, n_img, n_cap, d, scores, ld_scores);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+extern "C" int itr_order_backward_f32(const float* im, const float* s, const float* scores, int64_t ld_scores,
+                                      const float* d_scores, int64_t ld_dscores, int n_img, int n_cap, int d,
+                                      float* d_im, float* d_s, void* stream) {
+  ITR_REQUIRE(im && s && scores && d_scores, "itr_order_backward_f32: null pointer");
+  ITR_REQUIRE(n_img >= 0 && n_cap >= 0 && d > 0 && ld_scores >= n_cap && ld_dscores >= n_cap, "itr_order_backward_f32: bad shape");
+  ITR_REQUIRE(n_img <= 65535 && n_cap <= 65535, "itr_order_backward_f32: more than 65535 rows per call");
+  if (n_img == 0 || n_cap == 0) return ITR_OK;
+  cudaStream_t st = as_stream(stream);
+  if (d_im) order_backward_kernel<true><<<dim3((d + 255) / 256, n_img), 256, 0, st>>>(im, s, scores, ld_scores, d_scores, ld_dscores, n_img, n_cap, d, d_im);
+  if (d_s) order_backward_kernel<false><<<dim3((d + 255) / 256, n_cap), 256, 0, st>>>(im, s, scores, ld_scores, d_scores, ld_dscores, n_img, n_cap, d, d_s);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}

@@ -88,10 +88,48 @@ class _CosineScores(torch.autograd.Function):
         return d_im, d_s
 
 
+class _OrderScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, im, s):
+        scores = ops.order_scores(im, s)
+        ctx.save_for_backward(im, s, scores)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        im, s, scores = ctx.saved_tensors
+        return ops.order_backward(im, s, scores, g.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
 def order_sim(im, s, *args):
-    """Objectives.py:24-30 (out of the accelerated scope; kept so measure='order' still works)."""
-    ymx = s.unsqueeze(1).expand(s.size(0), im.size(0), s.size(1)) - im.unsqueeze(0).expand(s.size(0), im.size(0), s.size(1))
-    return -ymx.clamp(min=0).pow(2).sum(2).sqrt().t()
+    """Objectives.py:24-30: -|max(s - im, 0)|_2 for every (image, caption) pair, (n_img, n_cap)."""
+    if _needs_grad(im, s):
+        return _OrderScores.apply(im, s)
+    return ops.order_scores(im, s)
+
+
+class _MultiViewScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, imgs, caps):
+        scores, arg = ops.multiview_scores(imgs, caps, need_argmax=True)
+        ctx.save_for_backward(imgs, caps, arg)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        imgs, caps, arg = ctx.saved_tensors
+        return ops.multiview_backward(imgs, caps, g.contiguous(), arg, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
+class MultiViewMatching(nn.Module):
+    """CAMERA's similarity (Fusionmodule.py:670-692): the best of the image's views for every caption.
+    imgs (num_imgs, r, dim), caps (num_caps, dim) -> (num_imgs, num_caps); the reference's two branches
+    (square batch / per-caption loop) compute the same thing and are one kernel chain here."""
+
+    def forward(self, imgs, caps, *args, **kwargs):
+        if _needs_grad(imgs, caps):
+            return _MultiViewScores.apply(imgs, caps)
+        return ops.multiview_scores(imgs, caps)
 
 
 def _scan(images, captions, cap_lens, config, cross_attn):

@@ -47,6 +47,67 @@ def cosine_scores(im, s):
     return out
 
 
+def order_scores(im, s):
+    """order_sim, Objectives.py:24-30."""
+    im, s = _cuda_f32(im, "im"), _cuda_f32(s, "s")
+    if im.dim() != 2 or s.dim() != 2 or im.size(1) != s.size(1):
+        raise ValueError("order_sim expects (n_img, d) and (n_cap, d) embeddings, got {} and {}".format(
+            tuple(im.shape), tuple(s.shape)))
+    out = torch.empty(im.size(0), s.size(0), device=im.device, dtype=torch.float32)
+    with torch.cuda.device(im.device):
+        check(capi.lib().itr_order_scores_f32(ptr(im), ptr(s), im.size(0), s.size(0), im.size(1), ptr(out),
+                                              max(s.size(0), 1), stream_ptr()))
+    return out
+
+
+def order_backward(im, s, scores, d_scores, need_im=True, need_s=True):
+    im, s, scores, d_scores = (_cuda_f32(t, n) for t, n in ((im, "im"), (s, "s"), (scores, "scores"), (d_scores, "d_scores")))
+    d_im = torch.empty_like(im) if need_im else None
+    d_s = torch.empty_like(s) if need_s else None
+    with torch.cuda.device(im.device):
+        check(capi.lib().itr_order_backward_f32(ptr(im), ptr(s), ptr(scores), max(scores.stride(0), 1), ptr(d_scores),
+                                                max(d_scores.stride(0), 1), im.size(0), s.size(0), im.size(1), ptr(d_im),
+                                                ptr(d_s), stream_ptr()))
+    return d_im, d_s
+
+
+def multiview_scores(imgs, caps, need_argmax=False, max_workspace_bytes=1 << 30):
+    """MultiViewMatching.forward, Fusionmodule.py:670-692: imgs (n_img, n_views, d), caps (n_cap, d)."""
+    imgs, caps = _cuda_f32(imgs, "imgs"), _cuda_f32(caps, "caps")
+    if imgs.dim() != 3 or caps.dim() != 2 or imgs.size(2) != caps.size(1):
+        raise ValueError("MultiViewMatching expects (n_img, n_views, d) and (n_cap, d), got {} and {}".format(
+            tuple(imgs.shape), tuple(caps.shape)))
+    n_img, n_views, d = imgs.shape
+    n_cap = caps.size(0)
+    out = torch.empty(n_img, n_cap, device=imgs.device, dtype=torch.float32)
+    arg = torch.empty(n_img, n_cap, device=imgs.device, dtype=torch.int32) if need_argmax else None
+    if n_img == 0 or n_cap == 0:
+        return (out, arg) if need_argmax else out
+    chunk = max(1, min(n_img, 65535, max_workspace_bytes // (4 * n_views * n_cap)))
+    with torch.cuda.device(imgs.device):
+        ws = torch.empty(chunk * n_views * n_cap, device=imgs.device, dtype=torch.float32)
+        for i0 in range(0, n_img, chunk):
+            i1 = min(i0 + chunk, n_img)
+            check(capi.lib().itr_multiview_scores_f32(ptr(imgs[i0:i1]), ptr(caps), i1 - i0, n_views, n_cap, d, ptr(ws),
+                                                      ptr(out[i0:i1]), n_cap, ptr(arg[i0:i1]) if need_argmax else None,
+                                                      stream_ptr()))
+    return (out, arg) if need_argmax else out
+
+
+def multiview_backward(imgs, caps, d_scores, arg, need_imgs=True, need_caps=True):
+    imgs, caps, d_scores = _cuda_f32(imgs, "imgs"), _cuda_f32(caps, "caps"), _cuda_f32(d_scores, "d_scores")
+    n_img, n_views, d = imgs.shape
+    n_cap = caps.size(0)
+    d_imgs = torch.empty_like(imgs) if need_imgs else None
+    d_caps = torch.empty_like(caps) if need_caps else None
+    with torch.cuda.device(imgs.device):
+        ws = torch.empty(n_img * n_views * n_cap, device=imgs.device, dtype=torch.float32)
+        check(capi.lib().itr_multiview_backward_f32(ptr(imgs), ptr(caps), n_img, n_views, n_cap, d, ptr(d_scores),
+                                                    max(d_scores.stride(0), 1), ptr(arg), ptr(ws), ptr(d_imgs), ptr(d_caps),
+                                                    stream_ptr()))
+    return d_imgs, d_caps
+
+
 # ------------------------------------------------------------------------------ SCAN, fp32 mode
 def scan_scores_f32(images, captions, cap_lens, cross_attn, raw_feature_norm, agg_func, lambda_softmax, lambda_lse):
     images, captions = _cuda_f32(images, "images"), _cuda_f32(captions, "captions")

@@ -64,6 +64,23 @@ int         itr_device_supported(int device);
 int itr_cosine_scores_f32(const float* im, const float* s, int n_img, int n_cap, int d,
                           float* scores, int64_t ld_scores, void* stream);
 
+/* ---- order-embedding scores: order_sim(im, s), Objectives.py:24-30 ------------------------
+ * scores[i, c] = -sqrt(sum_d max(s[c, d] - im[i, d], 0)^2).  The backward returns the gradients autograd produces for
+ * sum(scores * d_scores) (zero where the distance is exactly 0); either output may be NULL. */
+int itr_order_scores_f32(const float* im, const float* s, int n_img, int n_cap, int d, float* scores, int64_t ld_scores,
+                         void* stream);
+int itr_order_backward_f32(const float* im, const float* s, const float* scores, int64_t ld_scores, const float* d_scores,
+                           int64_t ld_dscores, int n_img, int n_cap, int d, float* d_im, float* d_s, void* stream);
+
+/* ---- CAMERA multi-view scores: MultiViewMatching.forward, Fusionmodule.py:670-692 ----------
+ * scores[i, c] = max_v imgs[i, v, :] . caps[c, :]; argmax (optional, (n_img, n_cap) int32) records the winning view
+ * (first on ties), which is all the backward needs.  workspace: n_img * n_views * n_cap floats of device scratch. */
+int itr_multiview_scores_f32(const float* imgs, const float* caps, int n_img, int n_views, int n_cap, int d,
+                             float* workspace, float* scores, int64_t ld_scores, int32_t* argmax, void* stream);
+int itr_multiview_backward_f32(const float* imgs, const float* caps, int n_img, int n_views, int n_cap, int d,
+                               const float* d_scores, int64_t ld_dscores, const int32_t* argmax, float* workspace,
+                               float* d_imgs, float* d_caps, void* stream);
+
 /* ---- SCAN scores, float32 validation mode ---------------------------------------------
  * xattn_score_t2i / xattn_score_i2t + func_attention + cosine_similarity,
  * Objectives.py:329-372, 376-417, 421-476, 10-15; l2norm utils.py:11-15.

@@ -121,6 +121,42 @@ def scan_grad_case(O, name="scan_grad", n=6, lens=(9, 3, 14, 6, 11, 2), seed=105
     print(name, len(out), "arrays")
 
 
+def aux_sims_case(O, name="aux_sims", seed=106):
+    """order_sim (Objectives.py:24-30) and CAMERA MultiViewMatching (Fusionmodule.py:670-692): scores and the
+    gradients torch autograd gives for sum(scores * d_scores), float64, from the reference's own code."""
+    import importlib
+    F = importlib.import_module("itr.modalmodule.Fusionmodule")
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    n_img, n_cap, d = 19, 33, 96
+    im = torch.randn(n_img, d, generator=g).abs()
+    s = torch.randn(n_cap, d, generator=g).abs()
+    s[3] = im[5] * 0.5                                          # a pair with distance exactly 0 (s <= im everywhere)
+    im_bits, s_bits = bf16_bits(im), bf16_bits(s)
+    im, s = from_bits(im_bits).double(), from_bits(s_bits).double()
+    ds = torch.randn(n_img, n_cap, generator=g, dtype=torch.float64)
+    a, b = im.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    sc = O.order_sim(a, b)
+    mask = sc.detach() != 0                                     # autograd's sqrt'(0) is inf: pin the finite pairs only
+    (sc * ds * mask).sum().backward()
+    out.update({"order|im_bits": im_bits, "order|s_bits": s_bits, "order|d_scores": (ds * mask).numpy(), "order|scores": sc.detach().numpy(),
+                "order|d_im": torch.nan_to_num(a.grad, nan=0.0).numpy(), "order|d_s": torch.nan_to_num(b.grad, nan=0.0).numpy()})
+    mvm = F.MultiViewMatching()
+    for tag, n_i, n_c in (("square", 12, 12), ("rect", 7, 20)):
+        imgs = torch.nn.functional.normalize(torch.randn(n_i, 12, d, generator=g), dim=-1)
+        caps = torch.nn.functional.normalize(torch.randn(n_c, d, generator=g), dim=-1)
+        i_bits, c_bits = bf16_bits(imgs), bf16_bits(caps)
+        imgs, caps = from_bits(i_bits).double(), from_bits(c_bits).double()
+        ds = torch.randn(n_i, n_c, generator=g, dtype=torch.float64)
+        a, b = imgs.clone().requires_grad_(True), caps.clone().requires_grad_(True)
+        sc = mvm(a, b)
+        (sc * ds).sum().backward()
+        out.update({"mvm|%s|img_bits" % tag: i_bits, "mvm|%s|cap_bits" % tag: c_bits, "mvm|%s|d_scores" % tag: ds.numpy(),
+                    "mvm|%s|scores" % tag: sc.detach().numpy(), "mvm|%s|d_imgs" % tag: a.grad.numpy(), "mvm|%s|d_caps" % tag: b.grad.numpy()})
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, len(out), "arrays")
+
+
 def main():
     O, E = ref_loader.load()
     torch.set_num_threads(8)
@@ -128,14 +164,18 @@ def main():
     os.makedirs(gold, exist_ok=True)
     if "--only" in sys.argv:
         only = sys.argv[sys.argv.index("--only") + 1]
-        if only != "scan_grad":
-            raise SystemExit("--only supports: scan_grad")
-        scan_grad_case(O)
+        if only == "scan_grad":
+            scan_grad_case(O)
+        elif only == "aux_sims":
+            aux_sims_case(O)
+        else:
+            raise SystemExit("--only supports: scan_grad, aux_sims")
         return
 
     scan_case(O, "scan_small", n_img=8, lens=[16, 3, 12, 9, 5, 14, 7, 11, 16, 4, 13, 8], seed=101)
     scan_case(O, "scan_long", n_img=5, lens=[72, 40, 33], seed=102)
     scan_grad_case(O)
+    aux_sims_case(O)
 
     # cosine + hinge
     g = torch.Generator().manual_seed(103)

@@ -247,3 +247,48 @@ def test_encode_data_pinned_handoff_and_validate_step_flow():
             return iter(list(Loader.__iter__(self))[::-1])
     _, cap2, _ = ev.encode_data(m, Rev(), islength=False)
     np.testing.assert_array_equal(cap2, cap.numpy())
+
+
+# ----------------------------------------------------------------------------- order_sim / MultiViewMatching (row f4)
+def test_order_sim_forward_backward_golden():
+    g = load_golden("aux_sims")
+    im = torch.from_numpy(bits_to_f32(g["order|im_bits"])).cuda().requires_grad_(True)
+    s = torch.from_numpy(bits_to_f32(g["order|s_bits"])).cuda().requires_grad_(True)
+    sc = ob.order_sim(im, s)
+    np.testing.assert_allclose(sc.detach().cpu().numpy(), g["order|scores"], rtol=2e-6, atol=1e-6)
+    (sc * torch.from_numpy(g["order|d_scores"]).float().cuda()).sum().backward()
+    np.testing.assert_allclose(im.grad.cpu().numpy(), g["order|d_im"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(s.grad.cpu().numpy(), g["order|d_s"], rtol=1e-4, atol=2e-5)
+    # ContrastiveLoss(measure="order") dispatches to it (Objectives.py:45-46)
+    crit = ob.ContrastiveLoss(dict(name="VSE++"), margin=0.05, measure="order", max_violation=True)
+    n = 19
+    a, b = im.detach()[:n].clone().requires_grad_(True), s.detach()[:n].clone().requires_grad_(True)
+    loss = crit(a, b)
+    loss.backward()
+    want_loss, d_sc = so.hinge_loss(so.order_scores(a.detach().cpu().numpy(), b.detach().cpu().numpy()), 0.05, True)
+    np.testing.assert_allclose(loss.item(), want_loss, rtol=1e-5)
+    want_a, want_b = so.order_grads(a.detach().cpu().numpy(), b.detach().cpu().numpy(), d_sc)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), want_a, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), want_b, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["square", "rect"])
+def test_multiview_matching_forward_backward_golden(tag):
+    g = load_golden("aux_sims")
+    imgs = torch.from_numpy(bits_to_f32(g["mvm|%s|img_bits" % tag])).cuda().requires_grad_(True)
+    caps = torch.from_numpy(bits_to_f32(g["mvm|%s|cap_bits" % tag])).cuda().requires_grad_(True)
+    mvm = itr_b200.MultiViewMatching()
+    with torch.no_grad():
+        np.testing.assert_allclose(mvm(imgs, caps).cpu().numpy(), g["mvm|%s|scores" % tag], rtol=2e-6, atol=1e-6)
+        # chunked over images (small workspace): same numbers
+        np.testing.assert_allclose(ops.multiview_scores(imgs, caps, max_workspace_bytes=4 * 12 * caps.size(0) * 2).cpu().numpy(),
+                                   g["mvm|%s|scores" % tag], rtol=2e-6, atol=1e-6)
+    sc = mvm(imgs, caps)
+    (sc * torch.from_numpy(g["mvm|%s|d_scores" % tag]).float().cuda()).sum().backward()
+    np.testing.assert_allclose(imgs.grad.cpu().numpy(), g["mvm|%s|d_imgs" % tag], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(caps.grad.cpu().numpy(), g["mvm|%s|d_caps" % tag], rtol=1e-4, atol=2e-6)
+    # CAMERA's loss: TripletLoss over the multi-view scores (Models.py:628)
+    if tag == "square":
+        loss = ob.TripletLoss(margin=0.2, max_violation=True)(mvm(imgs.detach(), caps.detach()))
+        want, _ = so.hinge_loss(g["mvm|square|scores"], 0.2, True)
+        np.testing.assert_allclose(loss.item(), want, rtol=1e-5)

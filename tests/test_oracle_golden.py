@@ -133,3 +133,20 @@ def test_scan_hinge_gradient_oracle(direction, lam_sm, mv):
     _, d_im, d_cap = sb.coefficient_form(img, cap, lens, d_scores, direction, "clipped_l2norm", "LogSumExp", lam_sm, 6.0)
     np.testing.assert_allclose(d_im, g[key + "|d_im"], rtol=1e-6, atol=1e-7 * np.abs(d_im).max())
     np.testing.assert_allclose(d_cap, g[key + "|d_cap"], rtol=1e-6, atol=1e-7 * np.abs(d_cap).max())
+
+
+# ----------------------------------------------------------------------------- order_sim / MultiViewMatching (row f4)
+def test_order_and_multiview_oracles_match_reference():
+    g = load_golden("aux_sims")
+    im, s = bits_to_f32(g["order|im_bits"]), bits_to_f32(g["order|s_bits"])
+    np.testing.assert_allclose(so.order_scores(im, s), g["order|scores"], rtol=1e-12, atol=1e-14)
+    assert (g["order|scores"] == 0).sum() == 1                     # the planted zero-distance pair
+    d_im, d_s = so.order_grads(im, s, g["order|d_scores"])
+    np.testing.assert_allclose(d_im, g["order|d_im"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(d_s, g["order|d_s"], rtol=1e-10, atol=1e-12)
+    for tag in ("square", "rect"):
+        imgs, caps = bits_to_f32(g["mvm|%s|img_bits" % tag]), bits_to_f32(g["mvm|%s|cap_bits" % tag])
+        np.testing.assert_allclose(so.multiview_scores(imgs, caps), g["mvm|%s|scores" % tag], rtol=1e-12, atol=1e-14)
+        d_imgs, d_caps = so.multiview_grads(imgs, caps, g["mvm|%s|d_scores" % tag])
+        np.testing.assert_allclose(d_imgs, g["mvm|%s|d_imgs" % tag], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(d_caps, g["mvm|%s|d_caps" % tag], rtol=1e-10, atol=1e-12)

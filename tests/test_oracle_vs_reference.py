@@ -63,6 +63,12 @@ def test_install_patches_the_real_reference_modules(ref):
         crit = Models.Objectives.ContrastiveLoss(config={"name": "SCAN", "cross_attn": "i2t", "raw_feature_norm": "clipped_l2norm"},
                                                  margin=0.2, measure="cosine", max_violation=True)
         assert crit.sim is itr_b200.xattn_score_i2t
+        # measure="order" and CAMERA's multi-view matching
+        assert Models.Objectives.order_sim is itr_b200.order_sim
+        assert Models.Fusionmodule.MultiViewMatching is itr_b200.MultiViewMatching
+        assert Models.Objectives.ContrastiveLoss({"name": "VSE++"}, measure="order").sim is itr_b200.order_sim
     finally:
         itr_b200.uninstall()
     assert (O.cosine_sim, O.ContrastiveLoss, E.cal_sims, E.encode_data) == orig
+    from itr.modalmodule import Fusionmodule
+    assert Fusionmodule.MultiViewMatching is not itr_b200.MultiViewMatching and O.order_sim is not itr_b200.order_sim
