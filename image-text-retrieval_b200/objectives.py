@@ -141,6 +141,10 @@ def _scan(images, captions, cap_lens, config, cross_attn):
     if norm in ("l1norm", "clipped_l1norm"):
         # the reference raises NameError here (undefined l1norm_d, defect D4)
         raise ValueError("raw_feature_norm {!r} is not implemented by the reference either".format(norm))
+    if images.size(0) == 0 or captions.size(0) == 0:
+        if not images.is_cuda:
+            raise RuntimeError("images live on {}; itr_b200 runs on CUDA only (no CPU fallback)".format(images.device))
+        return torch.zeros(images.size(0), captions.size(0), device=images.device, dtype=torch.float32)
     if _needs_grad(images, captions):
         ln = ops.lengths_to_numpy(cap_lens, captions.size(0))
         return _ScanScores.apply(images, captions, ln, cross_attn, norm, agg, float(lam_sm), float(lam_lse))

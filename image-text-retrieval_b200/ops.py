@@ -41,6 +41,8 @@ def cosine_scores(im, s):
         raise ValueError("cosine_sim expects (n_img, d) and (n_cap, d) embeddings, got {} and {}".format(
             tuple(im.shape), tuple(s.shape)))
     out = torch.empty(im.size(0), s.size(0), device=im.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(im.device):
         check(capi.lib().itr_cosine_scores_f32(ptr(im), ptr(s), im.size(0), s.size(0), im.size(1), ptr(out),
                                                out.stride(0) if out.numel() else s.size(0), stream_ptr()))
@@ -54,6 +56,8 @@ def order_scores(im, s):
         raise ValueError("order_sim expects (n_img, d) and (n_cap, d) embeddings, got {} and {}".format(
             tuple(im.shape), tuple(s.shape)))
     out = torch.empty(im.size(0), s.size(0), device=im.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(im.device):
         check(capi.lib().itr_order_scores_f32(ptr(im), ptr(s), im.size(0), s.size(0), im.size(1), ptr(out),
                                               max(s.size(0), 1), stream_ptr()))
@@ -121,8 +125,10 @@ def scan_scores_f32(images, captions, cap_lens, cross_attn, raw_feature_norm, ag
     norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
     if cross_attn not in ("t2i", "i2t"):
         raise ValueError("unknown cross_attn: {}".format(cross_attn))
-    lens_dev = torch.from_numpy(ln).to(images.device)
     out = torch.empty(n_img, n_cap, device=images.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
+    lens_dev = torch.from_numpy(ln).to(images.device)
     L = capi.lib()
     with torch.cuda.device(images.device):
         gram = None

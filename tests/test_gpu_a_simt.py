@@ -292,3 +292,19 @@ def test_multiview_matching_forward_backward_golden(tag):
         loss = ob.TripletLoss(margin=0.2, max_violation=True)(mvm(imgs.detach(), caps.detach()))
         want, _ = so.hinge_loss(g["mvm|square|scores"], 0.2, True)
         np.testing.assert_allclose(loss.item(), want, rtol=1e-5)
+
+
+def test_empty_inputs_return_empty_matrices():
+    """Zero images or zero captions: every scorer returns an empty matrix of the right shape without launching."""
+    z_im, z_cap = torch.zeros(0, 36, 1024, device="cuda"), torch.zeros(0, 7, 1024, device="cuda")
+    im, cap = torch.rand(3, 36, 1024, device="cuda"), torch.rand(2, 7, 1024, device="cuda")
+    for c in (cfg(), cfg(itr_b200_precision="bf16"), cfg(cross_attn="i2t", itr_b200_precision="bf16")):
+        fn = ob.xattn_score_t2i if c["cross_attn"] == "t2i" else ob.xattn_score_i2t
+        assert tuple(fn(z_im, cap, [7, 3], c).shape) == (0, 2)
+        assert tuple(fn(im, z_cap, [], c).shape) == (3, 0)
+    assert tuple(ob.cosine_sim(torch.zeros(0, 64, device="cuda"), torch.rand(5, 64, device="cuda")).shape) == (0, 5)
+    assert tuple(ob.cosine_sim(torch.rand(5, 64, device="cuda"), torch.zeros(0, 64, device="cuda")).shape) == (5, 0)
+    assert tuple(ob.order_sim(torch.zeros(0, 64, device="cuda"), torch.rand(5, 64, device="cuda")).shape) == (0, 5)
+    assert tuple(itr_b200.MultiViewMatching()(torch.zeros(0, 12, 64, device="cuda"), torch.rand(5, 64, device="cuda")).shape) == (0, 5)
+    d_im, d_cap = ops.scan_backward_f32(z_im, cap, [7, 3], torch.zeros(0, 2, device="cuda"), "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    assert tuple(d_im.shape) == (0, 36, 1024) and not d_cap.any()
