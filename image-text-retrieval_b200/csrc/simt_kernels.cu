@@ -664,7 +664,7 @@ extern "C" int itr_scan_scores_f32(const float* images, const float* gram, const
   ITR_REQUIRE(cross_attn == ITR_T2I || cross_attn == ITR_I2T, "unknown cross_attn: %d", cross_attn);
   ITR_REQUIRE(feature_norm >= 0 && feature_norm <= ITR_NORM_NONE, "unknown first norm type: %d", feature_norm);
   ITR_REQUIRE(agg >= 0 && agg <= ITR_AGG_SUM, "unknown aggfunc: %d", agg);
-  ITR_REQUIRE(n_regions == ITR_REGIONS, "itr_scan_scores_f32: built for %d regions per image, got %d", ITR_REGIONS, n_regions);
+  ITR_REQUIRE(n_regions >= 1 && n_regions <= ITR_REGIONS, "itr_scan_scores_f32: 1 to %d regions per image, got %d", ITR_REGIONS, n_regions);
   ITR_REQUIRE(lmax >= 1 && lmax <= ITR_MAX_WORDS_F32, "itr_scan_scores_f32: padded caption width %d outside [1, %d]", lmax, ITR_MAX_WORDS_F32);
   ITR_REQUIRE(cross_attn == ITR_I2T || gram != nullptr, "itr_scan_scores_f32: t2i needs the region Gram");
   ITR_REQUIRE(d > 0 && ld_scores >= n_cap, "itr_scan_scores_f32: bad shape");

@@ -84,7 +84,7 @@ int itr_multiview_backward_f32(const float* imgs, const float* caps, int n_img, 
 /* ---- SCAN scores, float32 validation mode ---------------------------------------------
  * xattn_score_t2i / xattn_score_i2t + func_attention + cosine_similarity,
  * Objectives.py:329-372, 376-417, 421-476, 10-15; l2norm utils.py:11-15.
- * All five working raw_feature_norm modes x four agg_func x both directions.
+ * All five working raw_feature_norm modes x four agg_func x both directions; 1 to 36 regions per image, any embed size.
  * images (n_img, n_regions, d); captions (n_cap, lmax, d) zero padded; cap_lens (n_cap).
  * gram: (n_img, n_regions, n_regions) from itr_region_gram_f32 (needed for ITR_T2I; may be NULL for ITR_I2T). */
 int itr_region_gram_f32(const float* images, int n_img, int n_regions, int d, float* gram, void* stream);

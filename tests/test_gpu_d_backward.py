@@ -141,3 +141,30 @@ def test_backward_argument_errors():
                               "clipped_l2norm", "LogSumExp", 9.0, 6.0)
     with pytest.raises(ValueError):
         ops.scan_backward_f32(img, cap, [5, 5, 5], torch.zeros(4, 3, device="cuda"), "t2i", "l1norm", "LogSumExp", 9.0, 6.0)
+
+
+@pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
+@pytest.mark.parametrize("n_regions,d", [(20, 300), (7, 64), (36, 2048)])
+def test_other_region_counts_and_embed_sizes(direction, lam_sm, n_regions, d):
+    """Grid features / other encoders: any region count up to 36 and any embedding size (multiple of 4 for the
+    backward) run the float32 kernels, forward and backward."""
+    rng = np.random.default_rng(n_regions * 1000 + d)
+    n_img = 6
+    lens = np.array([5, 11, 2, 23, 8], dtype=np.int32)
+    V = rng.standard_normal((n_img, n_regions, d)); V /= np.linalg.norm(V, axis=-1, keepdims=True)
+    W = np.zeros((len(lens), int(lens.max()), d))
+    for c, n in enumerate(lens):
+        W[c, :n] = rng.standard_normal((n, d)) / d ** 0.5 + 0.6 * V[c % n_img, rng.integers(0, n_regions, n)]
+    V, W = V.astype(np.float32), W.astype(np.float32)
+    dS = rng.standard_normal((n_img, len(lens))).astype(np.float32)
+    want, want_im, want_cap = sb.autograd_grads(V, W, lens, dS, direction, "clipped_l2norm", "LogSumExp", lam_sm, 6.0)
+    img, cap = torch.from_numpy(V).cuda().requires_grad_(True), torch.from_numpy(W).cuda().requires_grad_(True)
+    fn = ob.xattn_score_t2i if direction == "t2i" else ob.xattn_score_i2t
+    scores = fn(img, cap, lens, cfg(cross_attn=direction, lambda_softmax=lam_sm))
+    np.testing.assert_allclose(scores.detach().cpu().numpy(), want, rtol=2e-5, atol=2e-6)
+    with torch.no_grad():       # the no-grad call takes the same float32 kernel (the tensor-core path is 36 x 1024 only)
+        np.testing.assert_allclose(fn(img, cap, lens, cfg(cross_attn=direction, lambda_softmax=lam_sm)).cpu().numpy(), want,
+                                   rtol=2e-5, atol=2e-6)
+    (scores * torch.from_numpy(dS).cuda()).sum().backward()
+    close(img.grad, want_im, msg="d_images")
+    close(cap.grad, want_cap, msg="d_captions")
