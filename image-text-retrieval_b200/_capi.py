@@ -15,7 +15,7 @@ ITR_OK, ITR_ERR_INVALID, ITR_ERR_CUDA, ITR_ERR_UNSUPPORTED = 0, 1, 2, 3
 T2I, I2T = 0, 1
 NORM_CODES = {"clipped_l2norm": 0, "l2norm": 1, "softmax": 2, "clipped": 3, "no_norm": 4}
 AGG_CODES = {"LogSumExp": 0, "Mean": 1, "Max": 2, "Sum": 3}
-REGIONS, EMBED, TILE_WORDS, TILE_IMAGES, GRAM_BYTES, MAX_WORDS_F32 = 36, 1024, 128, 4, 4752, 80
+REGIONS, EMBED, TILE_WORDS, TILE_IMAGES, GRAM_BYTES, MAX_WORDS_F32 = 36, 1024, 128, 4, 4752, 96
 
 _p, _i, _f, _l = C.c_void_p, C.c_int, C.c_float, C.c_int64
 

@@ -42,12 +42,14 @@ __global__ void __launch_bounds__(256)
 scan_bwd_coeff_kernel(ScanBwdParams p) {
   extern __shared__ __align__(16) float smem[];
   const int R = p.f.R, RT = SF_IMGS * R, LP = SF_LP;
-  float* Vs = smem;                            // SF_BK*148 (phase 1 only)
-  float* Ws = Vs + SF_BK * 148;                // SF_BK*84  (phase 1 only)
-  float* Araw = Ws + SF_BK * 84;               // RT*LP  raw affinities [img*R + region][word]
+  // Vs / Ws live only during phase 1 and Y only after it: they share the first region.
+  const int head = max(SF_BK * 148 + SF_BK * SF_WP, RT * LP);
+  float* Vs = smem;                            // SF_BK*148   (phase 1 only)
+  float* Ws = Vs + SF_BK * 148;                // SF_BK*SF_WP (phase 1 only)
+  float* Y = smem;                             // RT*LP  G alpha, then d xh, then d a
+  float* Araw = smem + head;                   // RT*LP  raw affinities [img*R + region][word]
   float* X = Araw + RT * LP;                   // RT*LP  xh, then alpha
-  float* Y = X + RT * LP;                      // RT*LP  G alpha, then d xh, then d a
-  float* Gctx = Y + RT * LP;                   // t2i: SF_IMGS*R*R; i2t: LP*LP
+  float* Gctx = X + RT * LP;                   // t2i: SF_IMGS*R*R; i2t: LP*LP
   const int g_floats = max(SF_IMGS * R * R, LP * LP);
   float* wnorm = Gctx + g_floats;              // SF_LMAX
   float* vnorm = wnorm + SF_LMAX;              // RT
@@ -81,7 +83,8 @@ scan_bwd_coeff_kernel(ScanBwdParams p) {
     case 2: scan_f32_gemm<2>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
     case 3: scan_f32_gemm<3>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
     case 4: scan_f32_gemm<4>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    default: scan_f32_gemm<5>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 5: scan_f32_gemm<5>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    default: scan_f32_gemm<6>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
   }
   __syncthreads();
 
@@ -519,8 +522,9 @@ extern "C" int itr_scan_backward_f32(const float* images, const float* gram, con
   const int RT = SF_IMGS * R;
   int g_floats = SF_IMGS * R * R;
   if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
-  const size_t smem = sizeof(float) * ((size_t)SF_BK * 148 + SF_BK * 84 + 3 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT +
-                                       7 * (size_t)SF_IMGS * SB_RS);
+  size_t head = (size_t)SF_BK * 148 + SF_BK * SF_WP;
+  if ((size_t)RT * SF_LP > head) head = (size_t)RT * SF_LP;
+  const size_t smem = sizeof(float) * (head + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + 7 * (size_t)SF_IMGS * SB_RS);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_bwd_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_cap, w.n_groups);
   ITR_REQUIRE(grid.y <= 65535, "itr_scan_backward_f32: more than %d images per call", 65535 * SF_IMGS);

@@ -8,7 +8,8 @@ namespace itr {
 
 constexpr int SF_IMGS = 4;
 constexpr int SF_BK = 32;
-constexpr int SF_LMAX = ITR_MAX_WORDS_F32;   // 80
+constexpr int SF_LMAX = ITR_MAX_WORDS_F32;   // 96
+constexpr int SF_WP = SF_LMAX + 4;           // row pitch of the word tile Ws
 constexpr int SF_LP = SF_LMAX + 1;           // padded row length of the A arrays
 
 struct ScanF32Params {
@@ -22,7 +23,7 @@ struct ScanF32Params {
 template <int CPT>
 __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, int n_rows, const float* W, int n,
                                               float* Vs, float* Ws, float* Araw, float* qn_w, float* vn2, float* Gcap) {
-  // Vs[SF_BK][148], Ws[SF_BK][84]; thread (ty, tx): rows ty*9..ty*9+8, cols tx + 16*c
+  // Vs[SF_BK][148], Ws[SF_BK][SF_WP]; thread (ty, tx): rows ty*9..ty*9+8, cols tx + 16*c
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int RT = SF_IMGS * p.R;    // 144 rows when R = 36
   const int rpt = (RT + 15) / 16;  // rows per thread (9)
@@ -39,18 +40,18 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
       if (r < n_rows && k0 + k < p.d) v = p.images[((int64_t)img0 * p.R + r) * p.d + k0 + k];
       Vs[k * 148 + r] = v;
     }
-    for (int e = tid; e < SF_LMAX * SF_BK; e += 256) {
+    for (int e = tid; e < CPT * 16 * SF_BK; e += 256) {      // only the columns this caption's tile uses
       int j = e / SF_BK, k = e % SF_BK;
       float v = 0.f;
       if (j < n && k0 + k < p.d) v = W[(int64_t)j * p.d + k0 + k];
-      Ws[k * 84 + j] = v;
+      Ws[k * SF_WP + j] = v;
     }
     __syncthreads();
 #pragma unroll 4
     for (int k = 0; k < SF_BK; ++k) {
       float wv[CPT];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) wv[c] = Ws[k * 84 + tx + 16 * c];
+      for (int c = 0; c < CPT; ++c) wv[c] = Ws[k * SF_WP + tx + 16 * c];
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         float vv = (i < rpt) ? Vs[k * 148 + ty * rpt + i] : 0.f;
@@ -61,7 +62,7 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
     // squared norms of words / regions, and the caption's word Gram (i2t only)
     if (tid < n) {
       float s = 0.f;
-      for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * 84 + tid], Ws[k * 84 + tid], s);
+      for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * SF_WP + tid], Ws[k * SF_WP + tid], s);
       wn_acc += s;
     }
     if (tid < RT) {
@@ -73,7 +74,7 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
       for (int o = tid; o < n * n; o += 256) {
         int a = o / n, b = o % n;
         float s = 0.f;
-        for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * 84 + a], Ws[k * 84 + b], s);
+        for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * SF_WP + a], Ws[k * SF_WP + b], s);
         Gcap[a * SF_LP + b] += s;
       }
     }

@@ -269,8 +269,8 @@ scan_f32_kernel(ScanF32Params p) {
   extern __shared__ __align__(16) float smem[];
   const int R = p.R, RT = SF_IMGS * R;
   float* Vs = smem;                           // SF_BK*148
-  float* Ws = Vs + SF_BK * 148;               // SF_BK*84
-  float* Araw = Ws + SF_BK * 84;              // RT*SF_LP   raw affinities [row = img*R + region][word]
+  float* Ws = Vs + SF_BK * 148;               // SF_BK*SF_WP
+  float* Araw = Ws + SF_BK * SF_WP;              // RT*SF_LP   raw affinities [row = img*R + region][word]
   float* X = Araw + RT * SF_LP;               // RT*SF_LP   normalised / exponentiated copy
   float* Gctx = X + RT * SF_LP;               // t2i: SF_IMGS*R*R region Grams; i2t: SF_LP*SF_LP word Gram
   const int g_floats = max(SF_IMGS * R * R, SF_LP * SF_LP);
@@ -300,7 +300,8 @@ scan_f32_kernel(ScanF32Params p) {
     case 2: scan_f32_gemm<2>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
     case 3: scan_f32_gemm<3>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
     case 4: scan_f32_gemm<4>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    default: scan_f32_gemm<5>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 5: scan_f32_gemm<5>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    default: scan_f32_gemm<6>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
   }
   __syncthreads();
 
@@ -675,7 +676,7 @@ extern "C" int itr_scan_scores_f32(const float* images, const float* gram, const
   int g_floats = SF_IMGS * n_regions * n_regions;
   if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
   int rs = n_regions > SF_LMAX ? n_regions : SF_LMAX;
-  size_t smem = sizeof(float) * ((size_t)SF_BK * 148 + SF_BK * 84 + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
+  size_t smem = sizeof(float) * ((size_t)SF_BK * 148 + SF_BK * SF_WP + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_cap, (n_img + SF_IMGS - 1) / SF_IMGS);
   ITR_REQUIRE(grid.y <= 65535, "itr_scan_scores_f32: more than %d images per call", 65535 * SF_IMGS);

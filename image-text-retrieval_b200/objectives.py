@@ -8,7 +8,7 @@ Precision modes (config key ``itr_b200_precision`` or env ``ITR_B200_PRECISION``
           kernel.  Scores within 1e-3 relative of the reference fed the same rounded inputs.
   "fp32"  CUDA-core float32 kernels: every mode / direction, within 1e-5 relative.
 Under autograd (SCAN training) the scores always come from the float32 kernel and the backward is the native
-closed-form kernel chain of csrc/scan_bwd.cu (captions up to 80 words).
+closed-form kernel chain of csrc/scan_bwd.cu (captions up to 96 words).
 Anything the bf16 kernel does not cover runs in fp32 mode -- on the GPU, never on the CPU.
 """
 from __future__ import annotations

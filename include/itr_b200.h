@@ -51,7 +51,7 @@ extern "C" {
 #define ITR_TILE_WORDS     128   /* rows of one packed word tile (= UMMA M) */
 #define ITR_TILE_IMAGES    4     /* images per accumulator tile (UMMA N = 4*36 = 144) */
 #define ITR_GRAM_BYTES     4752  /* bytes per image of the Gram pack: fp16 48x48 off-diagonal Gram in UMMA core-matrix order + 36 fp32 diagonal entries */
-#define ITR_MAX_WORDS_F32  80    /* longest caption the fp32 validation kernel accepts */
+#define ITR_MAX_WORDS_F32  96    /* longest caption the fp32 kernels (validation mode, training backward) accept */
 
 /* ---- library ------------------------------------------------------------------------- */
 const char* itr_last_error(void);

@@ -74,12 +74,12 @@ def test_contrastive_loss_scan_backward_golden(direction, lam_sm, mv):
 
 @pytest.mark.parametrize("direction,lam_sm", [("t2i", 9.0), ("i2t", 4.0)])
 def test_backward_seeded_batch_vs_oracle(direction, lam_sm):
-    """A ragged batch at embed 1024 with a partial image group, lengths from 1 to 80, gradient through autograd."""
+    """A ragged batch at embed 1024 with a partial image group, lengths from 1 to 96, gradient through autograd."""
     rng = np.random.default_rng(7)
     n_img, d = 10, 1024
-    lens = np.array([1, 80, 17, 33, 2, 64, 12, 9, 48, 5, 27], dtype=np.int32)
+    lens = np.array([1, 96, 17, 33, 2, 64, 12, 9, 81, 5, 27], dtype=np.int32)
     V = rng.standard_normal((n_img, 36, d)); V /= np.linalg.norm(V, axis=-1, keepdims=True)
-    W = np.zeros((len(lens), 80, d))
+    W = np.zeros((len(lens), 96, d))
     for c, n in enumerate(lens):
         W[c, :n] = rng.standard_normal((n, d)) / d ** 0.5 + 0.6 * V[c % n_img, rng.integers(0, 36, n)]
     V, W = V.astype(np.float32), W.astype(np.float32)
@@ -137,7 +137,7 @@ def test_backward_argument_errors():
     with pytest.raises(ValueError):
         ops.scan_backward_f32(img, cap, [5, 9, 5], torch.zeros(4, 3, device="cuda"), "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
     with pytest.raises(ValueError):
-        ops.scan_backward_f32(img, torch.zeros(3, 90, 64, device="cuda"), [5, 5, 5], torch.zeros(4, 3, device="cuda"), "i2t",
+        ops.scan_backward_f32(img, torch.zeros(3, 100, 64, device="cuda"), [5, 5, 5], torch.zeros(4, 3, device="cuda"), "i2t",
                               "clipped_l2norm", "LogSumExp", 9.0, 6.0)
     with pytest.raises(ValueError):
         ops.scan_backward_f32(img, cap, [5, 5, 5], torch.zeros(4, 3, device="cuda"), "t2i", "l1norm", "LogSumExp", 9.0, 6.0)
