@@ -43,9 +43,9 @@ scan_bwd_coeff_kernel(ScanBwdParams p) {
   extern __shared__ __align__(16) float smem[];
   const int R = p.f.R, RT = SF_IMGS * R, LP = SF_LP;
   // Vs / Ws live only during phase 1 and Y only after it: they share the first region.
-  const int head = max(SF_BK * 148 + SF_BK * SF_WP, RT * LP);
-  float* Vs = smem;                            // SF_BK*148   (phase 1 only)
-  float* Ws = Vs + SF_BK * 148;                // SF_BK*SF_WP (phase 1 only)
+  const int head = max(SF_VS_FLOATS + SF_WS_FLOATS, RT * LP);
+  float* Vs = smem;                            // SF_VS_FLOATS (phase 1 only)
+  float* Ws = Vs + SF_VS_FLOATS;               // SF_WS_FLOATS (phase 1 only)
   float* Y = smem;                             // RT*LP  G alpha, then d xh, then d a
   float* Araw = smem + head;                   // RT*LP  raw affinities [img*R + region][word]
   float* X = Araw + RT * LP;                   // RT*LP  xh, then alpha
@@ -522,7 +522,7 @@ extern "C" int itr_scan_backward_f32(const float* images, const float* gram, con
   const int RT = SF_IMGS * R;
   int g_floats = SF_IMGS * R * R;
   if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
-  size_t head = (size_t)SF_BK * 148 + SF_BK * SF_WP;
+  size_t head = (size_t)SF_VS_FLOATS + SF_WS_FLOATS;
   if ((size_t)RT * SF_LP > head) head = (size_t)RT * SF_LP;
   const size_t smem = sizeof(float) * (head + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + 7 * (size_t)SF_IMGS * SB_RS);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_bwd_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -9,7 +9,6 @@ namespace itr {
 constexpr int SF_IMGS = 4;
 constexpr int SF_BK = 32;
 constexpr int SF_LMAX = ITR_MAX_WORDS_F32;   // 96
-constexpr int SF_WP = SF_LMAX + 4;           // row pitch of the word tile Ws
 constexpr int SF_LP = SF_LMAX + 1;           // padded row length of the A arrays
 
 struct ScanF32Params {
@@ -20,13 +19,52 @@ struct ScanF32Params {
   float* scores; int64_t ld_scores;
 };
 
+// Shared-memory operand tiles of one k-slab, both k-fastest with a 4-float skew (16-byte aligned rows, so the inner
+// product reads float4 = 4 k-values per LDS): Vs[144 rows][SF_KP], Ws[96 rows][SF_KP].
+constexpr int SF_KP = SF_BK + 4;
+constexpr int SF_VS_FLOATS = 144 * SF_KP;
+constexpr int SF_WS_FLOATS = SF_LMAX * SF_KP;
+
+// one slab row (32 consecutive k) from global memory into a tile row; zero beyond the row / embedding bounds
+__device__ __forceinline__ void sf_load_rows(const float* __restrict__ src, int n_valid, int n_rows, int d, int k0, bool vec,
+                                             float* __restrict__ tile) {
+  for (int e = threadIdx.x; e < n_rows * (SF_BK / 4); e += 256) {
+    const int r = e >> 3, k = (e & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < n_valid) {
+      const float* g = src + (int64_t)r * d + k0 + k;
+      if (vec && k0 + k + 3 < d) {
+        v = *reinterpret_cast<const float4*>(g);
+      } else {
+        if (k0 + k + 0 < d) v.x = g[0];
+        if (k0 + k + 1 < d) v.y = g[1];
+        if (k0 + k + 2 < d) v.z = g[2];
+        if (k0 + k + 3 < d) v.w = g[3];
+      }
+    }
+    *reinterpret_cast<float4*>(tile + r * SF_KP + k) = v;
+  }
+}
+
+__device__ __forceinline__ float sf_dot_slab(const float* a, const float* b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < SF_BK; k += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(a + k), y = *reinterpret_cast<const float4*>(b + k);
+    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+  }
+  return s;
+}
+
 template <int CPT>
 __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, int n_rows, const float* W, int n,
                                               float* Vs, float* Ws, float* Araw, float* qn_w, float* vn2, float* Gcap) {
-  // Vs[SF_BK][148], Ws[SF_BK][SF_WP]; thread (ty, tx): rows ty*9..ty*9+8, cols tx + 16*c
+  // thread (ty, tx): region rows ty*rpt .. ty*rpt + rpt - 1, word columns tx + 16*c
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int RT = SF_IMGS * p.R;    // 144 rows when R = 36
   const int rpt = (RT + 15) / 16;  // rows per thread (9)
+  const float* V = p.images + (int64_t)img0 * p.R * p.d;
+  const bool vec = (p.d % 4 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   float acc[9][CPT];
 #pragma unroll
   for (int i = 0; i < 9; ++i)
@@ -34,48 +72,34 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
     for (int c = 0; c < CPT; ++c) acc[i][c] = 0.f;
   float wn_acc = 0.f, vn_acc = 0.f;
   for (int k0 = 0; k0 < p.d; k0 += SF_BK) {
-    for (int e = tid; e < RT * SF_BK; e += 256) {
-      int r = e / SF_BK, k = e % SF_BK;
-      float v = 0.f;
-      if (r < n_rows && k0 + k < p.d) v = p.images[((int64_t)img0 * p.R + r) * p.d + k0 + k];
-      Vs[k * 148 + r] = v;
-    }
-    for (int e = tid; e < CPT * 16 * SF_BK; e += 256) {      // only the columns this caption's tile uses
-      int j = e / SF_BK, k = e % SF_BK;
-      float v = 0.f;
-      if (j < n && k0 + k < p.d) v = W[(int64_t)j * p.d + k0 + k];
-      Ws[k * SF_WP + j] = v;
-    }
+    sf_load_rows(V, n_rows, 16 * rpt, p.d, k0, vec, Vs);
+    sf_load_rows(W, n, CPT * 16, p.d, k0, vec, Ws);          // only the columns this caption's tile uses
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < SF_BK; ++k) {
-      float wv[CPT];
+#pragma unroll 2
+    for (int k = 0; k < SF_BK; k += 4) {
+      float4 wv[CPT];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) wv[c] = Ws[k * SF_WP + tx + 16 * c];
+      for (int c = 0; c < CPT; ++c) wv[c] = *reinterpret_cast<const float4*>(Ws + (tx + 16 * c) * SF_KP + k);
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        float vv = (i < rpt) ? Vs[k * 148 + ty * rpt + i] : 0.f;
+        if (i < rpt) {
+          const float4 vv = *reinterpret_cast<const float4*>(Vs + (ty * rpt + i) * SF_KP + k);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(vv, wv[c], acc[i][c]);
+          for (int c = 0; c < CPT; ++c) {
+            float a = acc[i][c];
+            a = fmaf(vv.x, wv[c].x, a); a = fmaf(vv.y, wv[c].y, a); a = fmaf(vv.z, wv[c].z, a); a = fmaf(vv.w, wv[c].w, a);
+            acc[i][c] = a;
+          }
+        }
       }
     }
     // squared norms of words / regions, and the caption's word Gram (i2t only)
-    if (tid < n) {
-      float s = 0.f;
-      for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * SF_WP + tid], Ws[k * SF_WP + tid], s);
-      wn_acc += s;
-    }
-    if (tid < RT) {
-      float s = 0.f;
-      for (int k = 0; k < SF_BK; ++k) s = fmaf(Vs[k * 148 + tid], Vs[k * 148 + tid], s);
-      vn_acc += s;
-    }
+    if (tid < n) wn_acc += sf_dot_slab(Ws + tid * SF_KP, Ws + tid * SF_KP);
+    if (tid < RT) vn_acc += sf_dot_slab(Vs + tid * SF_KP, Vs + tid * SF_KP);
     if (p.cross_attn == ITR_I2T) {
       for (int o = tid; o < n * n; o += 256) {
-        int a = o / n, b = o % n;
-        float s = 0.f;
-        for (int k = 0; k < SF_BK; ++k) s = fmaf(Ws[k * SF_WP + a], Ws[k * SF_WP + b], s);
-        Gcap[a * SF_LP + b] += s;
+        const int a = o / n, b = o % n;
+        Gcap[a * SF_LP + b] += sf_dot_slab(Ws + a * SF_KP, Ws + b * SF_KP);
       }
     }
     __syncthreads();

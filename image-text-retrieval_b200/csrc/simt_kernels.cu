@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(256)
 scan_f32_kernel(ScanF32Params p) {
   extern __shared__ __align__(16) float smem[];
   const int R = p.R, RT = SF_IMGS * R;
-  float* Vs = smem;                           // SF_BK*148
-  float* Ws = Vs + SF_BK * 148;               // SF_BK*SF_WP
-  float* Araw = Ws + SF_BK * SF_WP;              // RT*SF_LP   raw affinities [row = img*R + region][word]
+  float* Vs = smem;                           // SF_VS_FLOATS
+  float* Ws = Vs + SF_VS_FLOATS;              // SF_WS_FLOATS
+  float* Araw = Ws + SF_WS_FLOATS;              // RT*SF_LP   raw affinities [row = img*R + region][word]
   float* X = Araw + RT * SF_LP;               // RT*SF_LP   normalised / exponentiated copy
   float* Gctx = X + RT * SF_LP;               // t2i: SF_IMGS*R*R region Grams; i2t: SF_LP*SF_LP word Gram
   const int g_floats = max(SF_IMGS * R * R, SF_LP * SF_LP);
@@ -676,7 +676,7 @@ extern "C" int itr_scan_scores_f32(const float* images, const float* gram, const
   int g_floats = SF_IMGS * n_regions * n_regions;
   if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
   int rs = n_regions > SF_LMAX ? n_regions : SF_LMAX;
-  size_t smem = sizeof(float) * ((size_t)SF_BK * 148 + SF_BK * SF_WP + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
+  size_t smem = sizeof(float) * ((size_t)SF_VS_FLOATS + SF_WS_FLOATS + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_cap, (n_img + SF_IMGS - 1) / SF_IMGS);
   ITR_REQUIRE(grid.y <= 65535, "itr_scan_scores_f32: more than %d images per call", 65535 * SF_IMGS);
