@@ -41,7 +41,8 @@ constexpr int SB_RS = SF_LMAX;     // per-image stride of the small per-query / 
 __global__ void __launch_bounds__(256)
 scan_bwd_coeff_kernel(ScanBwdParams p) {
   extern __shared__ __align__(16) float smem[];
-  const int R = p.f.R, RT = SF_IMGS * R, LP = SF_LP;
+  const int R = p.f.R, RT = SF_IMGS * R, LP = sf_pitch(p.f.lmax);
+  const bool t2i_ = (p.f.cross_attn == ITR_T2I);
   // Vs / Ws live only during phase 1 and Y only after it: they share the first region.
   const int head = max(SF_VS_FLOATS + SF_WS_FLOATS, RT * LP);
   float* Vs = smem;                            // SF_VS_FLOATS (phase 1 only)
@@ -50,7 +51,7 @@ scan_bwd_coeff_kernel(ScanBwdParams p) {
   float* Araw = smem + head;                   // RT*LP  raw affinities [img*R + region][word]
   float* X = Araw + RT * LP;                   // RT*LP  xh, then alpha
   float* Gctx = X + RT * LP;                   // t2i: SF_IMGS*R*R; i2t: LP*LP
-  const int g_floats = max(SF_IMGS * R * R, LP * LP);
+  const int g_floats = t2i_ ? SF_IMGS * R * R : LP * LP;
   float* wnorm = Gctx + g_floats;              // SF_LMAX
   float* vnorm = wnorm + SF_LMAX;              // RT
   float* rsim = vnorm + RT;                    // SF_IMGS*SB_RS   r_q
@@ -79,12 +80,12 @@ scan_bwd_coeff_kernel(ScanBwdParams p) {
   __syncthreads();
   const int cpt = (n + 15) / 16;
   switch (cpt) {
-    case 1: scan_f32_gemm<1>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 2: scan_f32_gemm<2>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 3: scan_f32_gemm<3>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 4: scan_f32_gemm<4>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 5: scan_f32_gemm<5>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    default: scan_f32_gemm<6>(p.f, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 1: scan_f32_gemm<1>(p.f, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 2: scan_f32_gemm<2>(p.f, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 3: scan_f32_gemm<3>(p.f, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 4: scan_f32_gemm<4>(p.f, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 5: scan_f32_gemm<5>(p.f, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    default: scan_f32_gemm<6>(p.f, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
   }
   __syncthreads();
 
@@ -519,12 +520,11 @@ extern "C" int itr_scan_backward_f32(const float* images, const float* gram, con
   p.d_scores = d_scores; p.ld_ds = ld_dscores; p.cap_off = cap_off; p.gram_off = gram_off;
   p.M = ws + w.m; p.ldm = w.ldm; p.MT = ws + w.mt; p.ldmt = rows;
   p.Tpart = ws + w.tpart; p.MCpart = ws + w.mcpart; p.n_words = n_words; p.sum_n2 = sum_len_sq;
-  const int RT = SF_IMGS * R;
-  int g_floats = SF_IMGS * R * R;
-  if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
+  const int RT = SF_IMGS * R, LP = sf_pitch(lmax);
+  const int g_floats = t2i ? SF_IMGS * R * R : LP * LP;
   size_t head = (size_t)SF_VS_FLOATS + SF_WS_FLOATS;
-  if ((size_t)RT * SF_LP > head) head = (size_t)RT * SF_LP;
-  const size_t smem = sizeof(float) * (head + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + 7 * (size_t)SF_IMGS * SB_RS);
+  if ((size_t)RT * LP > head) head = (size_t)RT * LP;
+  const size_t smem = sizeof(float) * (head + 2 * (size_t)RT * LP + g_floats + SF_LMAX + RT + 7 * (size_t)SF_IMGS * SB_RS);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_bwd_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_cap, w.n_groups);
   ITR_REQUIRE(grid.y <= 65535, "itr_scan_backward_f32: more than %d images per call", 65535 * SF_IMGS);

@@ -9,7 +9,9 @@ namespace itr {
 constexpr int SF_IMGS = 4;
 constexpr int SF_BK = 32;
 constexpr int SF_LMAX = ITR_MAX_WORDS_F32;   // 96
-constexpr int SF_LP = SF_LMAX + 1;           // padded row length of the A arrays
+constexpr int SF_LP = SF_LMAX + 1;           // largest padded row length of the A arrays
+// odd row pitch for a batch whose longest caption has lmax words (the i2t accesses stride by LP across lanes)
+__host__ __device__ inline int sf_pitch(int lmax) { return (lmax + 1) | 1; }
 
 struct ScanF32Params {
   const float* images; const float* gram; const float* captions; const int32_t* cap_lens;
@@ -57,7 +59,7 @@ __device__ __forceinline__ float sf_dot_slab(const float* a, const float* b) {
 }
 
 template <int CPT>
-__device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, int n_rows, const float* W, int n,
+__device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, int n_rows, const float* W, int n, int LP,
                                               float* Vs, float* Ws, float* Araw, float* qn_w, float* vn2, float* Gcap) {
   // thread (ty, tx): region rows ty*rpt .. ty*rpt + rpt - 1, word columns tx + 16*c
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -99,7 +101,7 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
     if (p.cross_attn == ITR_I2T) {
       for (int o = tid; o < n * n; o += 256) {
         const int a = o / n, b = o % n;
-        Gcap[a * SF_LP + b] += sf_dot_slab(Ws + a * SF_KP, Ws + b * SF_KP);
+        Gcap[a * LP + b] += sf_dot_slab(Ws + a * SF_KP, Ws + b * SF_KP);
       }
     }
     __syncthreads();
@@ -111,7 +113,7 @@ __device__ __forceinline__ void scan_f32_gemm(const ScanF32Params& p, int img0, 
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         int j = tx + 16 * c;
-        if (j < SF_LMAX) Araw[r * SF_LP + j] = acc[i][c];
+        if (j < LP) Araw[r * LP + j] = acc[i][c];
       }
     }
   }

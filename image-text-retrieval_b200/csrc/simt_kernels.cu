@@ -267,13 +267,13 @@ __device__ __forceinline__ void scan_epilogue_smem(const ScanEpiParams& p, int n
 __global__ void __launch_bounds__(256)
 scan_f32_kernel(ScanF32Params p) {
   extern __shared__ __align__(16) float smem[];
-  const int R = p.R, RT = SF_IMGS * R;
+  const int R = p.R, RT = SF_IMGS * R, LP = sf_pitch(p.lmax);
   float* Vs = smem;                           // SF_VS_FLOATS
   float* Ws = Vs + SF_VS_FLOATS;              // SF_WS_FLOATS
-  float* Araw = Ws + SF_WS_FLOATS;              // RT*SF_LP   raw affinities [row = img*R + region][word]
-  float* X = Araw + RT * SF_LP;               // RT*SF_LP   normalised / exponentiated copy
-  float* Gctx = X + RT * SF_LP;               // t2i: SF_IMGS*R*R region Grams; i2t: SF_LP*SF_LP word Gram
-  const int g_floats = max(SF_IMGS * R * R, SF_LP * SF_LP);
+  float* Araw = Ws + SF_WS_FLOATS;            // RT*LP   raw affinities [row = img*R + region][word]
+  float* X = Araw + RT * LP;                  // RT*LP   normalised / exponentiated copy
+  float* Gctx = X + RT * LP;                  // t2i: SF_IMGS*R*R region Grams; i2t: LP*LP word Gram
+  const int g_floats = (p.cross_attn == ITR_T2I) ? SF_IMGS * R * R : LP * LP;
   float* wnorm = Gctx + g_floats;             // SF_LMAX  |w_j|
   float* vnorm = wnorm + SF_LMAX;             // RT       |v_k|
   float* rsim = vnorm + RT;                   // SF_IMGS * max(R, SF_LMAX)
@@ -290,23 +290,23 @@ scan_f32_kernel(ScanF32Params p) {
   if (t2i) {
     for (int e = tid; e < n_im * R * R; e += 256) Gctx[e] = p.gram[(int64_t)img0 * R * R + e];
   } else {
-    for (int e = tid; e < SF_LP * SF_LP; e += 256) Gctx[e] = 0.f;
+    for (int e = tid; e < LP * LP; e += 256) Gctx[e] = 0.f;
   }
   __syncthreads();
 
   const int cpt = (n + 15) / 16;
   switch (cpt) {
-    case 1: scan_f32_gemm<1>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 2: scan_f32_gemm<2>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 3: scan_f32_gemm<3>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 4: scan_f32_gemm<4>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    case 5: scan_f32_gemm<5>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
-    default: scan_f32_gemm<6>(p, img0, n_im * R, W, n, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 1: scan_f32_gemm<1>(p, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 2: scan_f32_gemm<2>(p, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 3: scan_f32_gemm<3>(p, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 4: scan_f32_gemm<4>(p, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    case 5: scan_f32_gemm<5>(p, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
+    default: scan_f32_gemm<6>(p, img0, n_im * R, W, n, LP, Vs, Ws, Araw, wnorm, vnorm, Gctx); break;
   }
   __syncthreads();
 
   ScanEpiParams ep{R, p.cross_attn, p.feature_norm, p.agg, p.lambda_softmax, p.lambda_lse, p.scores, p.ld_scores};
-  scan_epilogue_smem(ep, n_im, n, img0, c, SF_LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
+  scan_epilogue_smem(ep, n_im, n, img0, c, LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
 }
 
 // =========================================================================================
@@ -672,11 +672,10 @@ extern "C" int itr_scan_scores_f32(const float* images, const float* gram, const
   if (n_img <= 0 || n_cap <= 0) return ITR_OK;
   ScanF32Params p{images, gram, captions, cap_lens, n_img, n_regions, n_cap, lmax, d,
                   cross_attn, feature_norm, agg, lambda_softmax, lambda_lse, scores, ld_scores};
-  const int RT = SF_IMGS * n_regions;
-  int g_floats = SF_IMGS * n_regions * n_regions;
-  if (SF_LP * SF_LP > g_floats) g_floats = SF_LP * SF_LP;
+  const int RT = SF_IMGS * n_regions, LP = sf_pitch(lmax);
+  const int g_floats = (cross_attn == ITR_T2I) ? SF_IMGS * n_regions * n_regions : LP * LP;
   int rs = n_regions > SF_LMAX ? n_regions : SF_LMAX;
-  size_t smem = sizeof(float) * ((size_t)SF_VS_FLOATS + SF_WS_FLOATS + 2 * (size_t)RT * SF_LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
+  size_t smem = sizeof(float) * ((size_t)SF_VS_FLOATS + SF_WS_FLOATS + 2 * (size_t)RT * LP + g_floats + SF_LMAX + RT + SF_IMGS * rs);
   ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_cap, (n_img + SF_IMGS - 1) / SF_IMGS);
   ITR_REQUIRE(grid.y <= 65535, "itr_scan_scores_f32: more than %d images per call", 65535 * SF_IMGS);
