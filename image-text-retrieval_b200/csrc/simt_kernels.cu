@@ -367,6 +367,154 @@ scan_epilogue_kernel(ScanEpiKernelParams p) {
   scan_epilogue_smem(p.e, n_im, n, img0, c, LP, Araw, X, Gctx, wnorm, vnorm, rsim, RS);
 }
 
+// i2t, captions of at most NMAX <= 32 words (all but a handful): the same phase 2 with the softmax-over-words step
+// specialised.  In the i2t layout a thread's (image, region) column is a contiguous shared-memory row, so its NMAX
+// attention weights live in registers, the word Gram is read as broadcast float4 and alpha^T G alpha is fully
+// unrolled over the strict upper triangle.  One block = one caption x 7 images (252 of 256 threads busy).
+constexpr int I2T_IMGS = 7;
+
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+scan_i2t_epilogue_kernel(ScanEpiKernelParams p) {
+  constexpr int R = ITR_REGIONS, RT = I2T_IMGS * R, LP = NMAX + 1;     // odd pitch
+  extern __shared__ __align__(16) float smem[];
+  float* Araw = smem;                          // RT*LP  [img*R + region][word]
+  float* X = Araw + RT * LP;                   // RT*LP
+  float* G = X + RT * LP;                      // NMAX*NMAX word Gram, zero padded
+  float* vnorm = G + NMAX * NMAX;              // RT
+  float* rsim = vnorm + RT;                    // RT
+  const int c = p.cap_ids ? p.cap_ids[blockIdx.x] : (int)blockIdx.x;
+  const int img0 = blockIdx.y * I2T_IMGS, tid = threadIdx.x;
+  const int n_im = min(I2T_IMGS, p.n_img - img0);
+  const int n = p.cap_lens[c];
+  const int row0 = p.cap_row0[c];
+  const int tile = row0 / ITR_TILE_WORDS, r_in = row0 % ITR_TILE_WORDS;
+  const int mode = p.e.feature_norm;
+
+  for (int m = 0; m < n_im; ++m) {
+    const float* src = p.affinity + (((size_t)tile * p.n_img + img0 + m) * ITR_TILE_WORDS + r_in) * R;
+    float* dst = Araw + m * R * LP;
+    for (int e = tid; e < n * R; e += 256) {
+      const int j = e / R, k = e - j * R;
+      dst[k * LP + j] = src[e];
+    }
+  }
+  {
+    const float* g = p.cap_gram + p.gram_off[c];
+    for (int e = tid; e < NMAX * NMAX; e += 256) {
+      const int a = e / NMAX, b = e - a * NMAX;
+      G[e] = (a < n && b < n) ? g[a * n + b] : 0.f;
+    }
+  }
+  for (int e = tid; e < n_im * R; e += 256) vnorm[e] = p.region_norm[(size_t)img0 * R + e];
+  __syncthreads();
+
+  // ---- step 1: raw_feature_norm over the 36 regions, for every (image, word) ---------------------
+  for (int it = tid; it < n_im * n; it += 256) {
+    const int m = it / n, s = it - m * n;
+    const float* a = Araw + m * R * LP + s;
+    float* x = X + m * R * LP + s;
+    if (mode == ITR_NORM_CLIPPED_L2 || mode == ITR_NORM_L2) {
+      float ss = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < R; ++q) {
+        float v = a[q * LP];
+        if (mode == ITR_NORM_CLIPPED_L2) v = leaky01(v);
+        ss = fmaf(v, v, ss);
+      }
+      const float inv = 1.f / (sqrtf(ss) + 1e-8f);
+#pragma unroll 4
+      for (int q = 0; q < R; ++q) {
+        float v = a[q * LP];
+        if (mode == ITR_NORM_CLIPPED_L2) v = leaky01(v);
+        x[q * LP] = v * inv;
+      }
+    } else if (mode == ITR_NORM_SOFTMAX) {
+      float mx = -FLT_MAX;
+      for (int q = 0; q < R; ++q) mx = fmaxf(mx, a[q * LP]);
+      float z = 0.f;
+      for (int q = 0; q < R; ++q) z += expf(a[q * LP] - mx);
+      const float inv = 1.f / z;
+      for (int q = 0; q < R; ++q) x[q * LP] = expf(a[q * LP] - mx) * inv;
+    } else {
+      for (int q = 0; q < R; ++q) {
+        const float v = a[q * LP];
+        x[q * LP] = (mode == ITR_NORM_CLIPPED) ? leaky01(v) : v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- step 2: softmax over the caption's words, attended cosine, one thread per (image, region) ----
+  if (tid < n_im * R) {
+    const float* a = Araw + tid * LP;
+    const float* x = X + tid * LP;
+    const float c2 = p.e.lambda_softmax * 1.4426950408889634f;      // exp(l x) = exp2(l log2e x)
+    float al[NMAX];
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int s = 0; s < NMAX; ++s) {
+      al[s] = (s < n) ? x[s] * c2 : -FLT_MAX;
+      mx = fmaxf(mx, al[s]);
+    }
+    float Z = 0.f;
+#pragma unroll
+    for (int s = 0; s < NMAX; ++s) {
+      al[s] = (s < n) ? exp2f(al[s] - mx) : 0.f;
+      Z += al[s];
+    }
+    const float invZ = 1.f / Z;
+    float P = 0.f;
+#pragma unroll
+    for (int s = 0; s < NMAX; ++s) {
+      al[s] *= invZ;
+      if (s < n) P = fmaf(al[s], a[s], P);
+    }
+    float Qf = 0.f;
+#pragma unroll
+    for (int s = 0; s < NMAX; ++s) {
+      float u = 0.f;
+#pragma unroll
+      for (int s2 = s + 1; s2 < NMAX; ++s2) u = fmaf(G[s * NMAX + s2], al[s2], u);
+      Qf = fmaf(al[s], fmaf(G[s * NMAX + s], al[s], 2.f * u), Qf);
+    }
+    const float w2 = sqrtf(fmaxf(Qf, 0.f));
+    rsim[tid] = P / fmaxf(vnorm[tid] * w2, 1e-8f);
+  }
+  __syncthreads();
+
+  // ---- step 3: aggregate over the 36 regions, one warp per image -----------------------------------
+  const int lane = tid & 31;
+  for (int m = tid >> 5; m < n_im; m += 8) {
+    const float* r = rsim + m * R;
+    float v;
+    if (p.e.agg == ITR_AGG_MAX) {
+      v = -FLT_MAX;
+      for (int q = lane; q < R; q += 32) v = fmaxf(v, r[q]);
+      v = warp_max(v);
+    } else {
+      v = 0.f;
+      for (int q = lane; q < R; q += 32) v += (p.e.agg == ITR_AGG_LSE) ? expf(r[q] * p.e.lambda_lse) : r[q];
+      v = warp_sum(v);
+      if (p.e.agg == ITR_AGG_LSE) v = logf(v) / p.e.lambda_lse;
+      if (p.e.agg == ITR_AGG_MEAN) v = v / (float)R;
+    }
+    if (lane == 0) p.e.scores[(int64_t)(img0 + m) * p.e.ld_scores + c] = v;
+  }
+}
+
+template <int NMAX>
+static int launch_i2t_epilogue(const ScanEpiKernelParams& p, int n_ids, int n_img, cudaStream_t st) {
+  constexpr int RT = I2T_IMGS * ITR_REGIONS, LP = NMAX + 1;
+  const size_t smem = sizeof(float) * (2 * (size_t)RT * LP + NMAX * NMAX + 2 * RT);
+  ITR_CHECK_CUDA(cudaFuncSetAttribute(scan_i2t_epilogue_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_ids, (n_img + I2T_IMGS - 1) / I2T_IMGS);
+  ITR_REQUIRE(grid.y <= 65535, "itr_scan_epilogue_f32: more than %d images per call", 65535 * I2T_IMGS);
+  scan_i2t_epilogue_kernel<NMAX><<<grid, 256, smem, st>>>(p);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
 // Word Gram of every caption from the packed bf16 rows: gram[gram_off[c] + j*n + j2] = w_j . w_j2 (fp32 accumulate).
 __global__ void __launch_bounds__(128)
 caption_gram_kernel(const uint16_t* __restrict__ words, const int32_t* __restrict__ cap_row0, const int32_t* __restrict__ cap_lens,
@@ -811,6 +959,16 @@ extern "C" int itr_scan_epilogue_f32(const float* affinity, int n_img, const int
     const int rs = R > LP ? R : LP;
     return sizeof(float) * (2 * (size_t)RT * LP + g_floats + LP + RT + (size_t)imgs * rs);
   };
+  if (cross_attn == ITR_I2T && max_len <= 32) {        // the specialised kernel: words in registers
+    ScanEpiKernelParams q{affinity, n_img, cap_row0, cap_lens, cap_ids, n_ids, 0, I2T_IMGS, row_wnorm, region_norm, region_gram, cap_gram,
+                          gram_off, ScanEpiParams{R, cross_attn, feature_norm, agg, lambda_softmax, lambda_lse, scores, ld_scores}};
+    cudaStream_t st = as_stream(stream);
+    if (max_len <= 8) return launch_i2t_epilogue<8>(q, n_ids, n_img, st);
+    if (max_len <= 12) return launch_i2t_epilogue<12>(q, n_ids, n_img, st);
+    if (max_len <= 16) return launch_i2t_epilogue<16>(q, n_ids, n_img, st);
+    if (max_len <= 24) return launch_i2t_epilogue<24>(q, n_ids, n_img, st);
+    return launch_i2t_epilogue<32>(q, n_ids, n_img, st);
+  }
   int imgs = SF_IMGS;
   if (cross_attn == ITR_I2T && smem_for(7) <= 110 * 1024) imgs = 7;
   const size_t smem = smem_for(imgs);
