@@ -391,14 +391,6 @@ scan_i2t_epilogue_kernel(ScanEpiKernelParams p) {
   const int tile = row0 / ITR_TILE_WORDS, r_in = row0 % ITR_TILE_WORDS;
   const int mode = p.e.feature_norm;
 
-  for (int m = 0; m < n_im; ++m) {
-    const float* src = p.affinity + (((size_t)tile * p.n_img + img0 + m) * ITR_TILE_WORDS + r_in) * R;
-    float* dst = Araw + m * R * LP;
-    for (int e = tid; e < n * R; e += 256) {
-      const int j = e / R, k = e - j * R;
-      dst[k * LP + j] = src[e];
-    }
-  }
   {
     const float* g = p.cap_gram + p.gram_off[c];
     for (int e = tid; e < NMAX * NMAX; e += 256) {
@@ -407,40 +399,47 @@ scan_i2t_epilogue_kernel(ScanEpiKernelParams p) {
     }
   }
   for (int e = tid; e < n_im * R; e += 256) vnorm[e] = p.region_norm[(size_t)img0 * R + e];
-  __syncthreads();
 
-  // ---- step 1: raw_feature_norm over the 36 regions, for every (image, word) ---------------------
+  // ---- load + step 1: one thread per (image, word).  The word's 36 affinities are one contiguous, 16-byte aligned
+  // 144-byte row of the dump: nine float4 loads, raw_feature_norm over the regions in registers, then the
+  // transposed scatter into the [region][word] tiles (lanes = consecutive words: conflict-free).
   for (int it = tid; it < n_im * n; it += 256) {
     const int m = it / n, s = it - m * n;
-    const float* a = Araw + m * R * LP + s;
+    const float4* src = reinterpret_cast<const float4*>(
+        p.affinity + (((size_t)tile * p.n_img + img0 + m) * ITR_TILE_WORDS + r_in + s) * R);
+    float v[R];
+#pragma unroll
+    for (int q4 = 0; q4 < R / 4; ++q4) {
+      const float4 t = src[q4];
+      v[q4 * 4 + 0] = t.x; v[q4 * 4 + 1] = t.y; v[q4 * 4 + 2] = t.z; v[q4 * 4 + 3] = t.w;
+    }
+    float* a = Araw + m * R * LP + s;
     float* x = X + m * R * LP + s;
+#pragma unroll
+    for (int q = 0; q < R; ++q) a[q * LP] = v[q];
     if (mode == ITR_NORM_CLIPPED_L2 || mode == ITR_NORM_L2) {
       float ss = 0.f;
-#pragma unroll 4
+#pragma unroll
       for (int q = 0; q < R; ++q) {
-        float v = a[q * LP];
-        if (mode == ITR_NORM_CLIPPED_L2) v = leaky01(v);
-        ss = fmaf(v, v, ss);
+        if (mode == ITR_NORM_CLIPPED_L2) v[q] = leaky01(v[q]);
+        ss = fmaf(v[q], v[q], ss);
       }
       const float inv = 1.f / (sqrtf(ss) + 1e-8f);
-#pragma unroll 4
-      for (int q = 0; q < R; ++q) {
-        float v = a[q * LP];
-        if (mode == ITR_NORM_CLIPPED_L2) v = leaky01(v);
-        x[q * LP] = v * inv;
-      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) x[q * LP] = v[q] * inv;
     } else if (mode == ITR_NORM_SOFTMAX) {
       float mx = -FLT_MAX;
-      for (int q = 0; q < R; ++q) mx = fmaxf(mx, a[q * LP]);
+#pragma unroll
+      for (int q = 0; q < R; ++q) mx = fmaxf(mx, v[q]);
       float z = 0.f;
-      for (int q = 0; q < R; ++q) z += expf(a[q * LP] - mx);
+#pragma unroll
+      for (int q = 0; q < R; ++q) { v[q] = expf(v[q] - mx); z += v[q]; }
       const float inv = 1.f / z;
-      for (int q = 0; q < R; ++q) x[q * LP] = expf(a[q * LP] - mx) * inv;
+#pragma unroll
+      for (int q = 0; q < R; ++q) x[q * LP] = v[q] * inv;
     } else {
-      for (int q = 0; q < R; ++q) {
-        const float v = a[q * LP];
-        x[q * LP] = (mode == ITR_NORM_CLIPPED) ? leaky01(v) : v;
-      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) x[q * LP] = (mode == ITR_NORM_CLIPPED) ? leaky01(v[q]) : v[q];
     }
   }
   __syncthreads();
