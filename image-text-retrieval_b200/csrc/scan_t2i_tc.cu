@@ -315,6 +315,7 @@ struct Params {
   long long* prof;             // optional [grid][16] cycle counters (see itr_scan_t2i_profile)
   int ctrl_last;               // 1: the control warpgroup is the LAST one (highest warp ids), 0: the first
   int skip_math;               // tuning only: epilogue loads and releases the accumulator, no arithmetic
+  int wait_mode;               // tuning only (PROF builds): 1 producer spins on `empty`, 2 MMA issuer spins on `full`
 };
 
 // inclusive segmented scan over the lanes [seg_lo, lane], then broadcast of the segment total
@@ -402,7 +403,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       const int row_w = (DEBUG ? p.dbg_m : item.m) * BLOCK_M, row_i = (DEBUG ? p.dbg_n : item.n) * BLOCK_N;
 #pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
-        mbar_wait_sleep_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
+        if (PROF && (p.wait_mode & 1)) mbar_wait_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
+        else mbar_wait_sleep_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
         const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES, fb = full_bar(stage);
         if (elect_one()) {
           if (PROF && (p.skip_math & 2)) {       // tuning only: no operand traffic at all (stale SMEM)
@@ -434,7 +436,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       tc_fence_after();
 #pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
-        mbar_wait_sleep_t(full_bar(stage), phase, w_full, prof_on);
+        if (PROF && (p.wait_mode & 2)) mbar_wait_t(full_bar(stage), phase, w_full, prof_on);
+        else mbar_wait_sleep_t(full_bar(stage), phase, w_full, prof_on);
         tc_fence_after();
         const uint64_t soff = (uint64_t)((uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4));
         const uint64_t adesc = adesc0 + soff, bdesc = bdesc0 + soff;
@@ -1002,7 +1005,8 @@ static int launch_tc(const uint16_t* images_bf16, const void* gram_pack, int n_i
     static int env_ctrl_last = -1;
     if (env_ctrl_last < 0) { const char* e = getenv("ITR_B200_CTRL_LAST"); env_ctrl_last = e ? atoi(e) : 1; }
     p.ctrl_last = mode >= 0 ? (mode & 1) : env_ctrl_last;
-    p.skip_math = mode >= 0 ? ((mode >> 1) & 63) : 0;    // tuning bits: 1 no epilogue arithmetic, 2 no TMA loads, 4 no scan, 8 no exp, 16 no phase-B dot
+    p.skip_math = mode >= 0 ? ((mode >> 1) & 63) : 0;
+    p.wait_mode = mode >= 0 ? ((mode >> 7) & 3) : 0;    // tuning bits: 1 no epilogue arithmetic, 2 no TMA loads, 4 no scan, 8 no exp, 16 no phase-B dot
   }
   int dev = 0, sms = 0;
   ITR_CHECK_CUDA(cudaGetDevice(&dev));

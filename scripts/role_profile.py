@@ -13,7 +13,7 @@ out = torch.empty(n_img, n_cap, device="cuda")
 names = ["producer total", "producer wait empty", "mma total", "mma wait tempty", "mma wait full", "items",
          "g0 wait tfull+afull", "g0 wait uready", "g1 wait tfull+afull", "g1 wait uready", "g2 wait tfull+afull", "g2 wait uready",
          "g3 wait tfull+afull", "g3 wait uready", "epilogue total", "g0 wait afull"]
-for mode in (1, 3):
+for mode in [int(m) for m in sys.argv[3].split(',')] if len(sys.argv) > 3 else (1, 3):
     cnt = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for rep in range(2):
