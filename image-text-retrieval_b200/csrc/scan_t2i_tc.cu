@@ -74,9 +74,14 @@ constexpr int XCH_FLOATS = 4 /*group*/ * 4 /*warp*/ * 40;
 // TMEM columns: [0,144) the accumulator (single buffer: it is released as soon as every epilogue
 // warp holds its 36 raw affinities in registers); [160,352) four 48-column Gram products U_g;
 // [352,472) four 24-column parking areas for the fp16 softmax numerators (32-column pitch).
-constexpr int U_BASE = 160;
-constexpr int PARK_BASE = 352;
-constexpr int PARK_PITCH = 32;
+// Tensor memory (512 columns): two accumulators [0,144) and [144,288), four Gram products at 288 + 48 g.
+// The fp16 numerators e(t) of group g are parked INSIDE the accumulator the item came from, in 24 of the group's own
+// 36 columns (the group has its raw affinities in registers by then), so a second accumulator fits.
+constexpr int ACC_PITCH = BLOCK_N;               // 144
+constexpr int U_BASE = 2 * ACC_PITCH;            // 288
+__host__ __device__ constexpr int park_col(int g) { return g == 0 ? 0 : 16 * ((36 * g + 15) / 16); }   // 0, 48, 80, 112
+static_assert(park_col(1) >= 36 && park_col(1) + 24 <= 72 && park_col(2) >= 72 && park_col(2) + 24 <= 108 &&
+              park_col(3) >= 108 && park_col(3) + 24 <= 144, "parking area must stay inside the group's own columns");
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 64;                       // word tiles kept L2-resident while images stream
 constexpr int NUM_THREADS = 640;
@@ -87,7 +92,7 @@ constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_XCH = SMEM_AUX + 2 * AUX_BYTES;
 constexpr int SMEM_BARS = SMEM_XCH + XCH_FLOATS * 4;
-constexpr int NUM_BARS = 2 * STAGES + 16;
+constexpr int NUM_BARS = 2 * STAGES + 18;
 constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for manual 1024-byte alignment
@@ -354,8 +359,9 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   const uint32_t bar0 = sbase + SMEM_BARS;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES + 0);
-  const uint32_t tempty_bar = bar0 + 8u * (2 * STAGES + 1);
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 0 + b); };     // accumulator b complete
+  auto loaded_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };    // all 16 epilogue warps hold accumulator b in registers
+  auto gfree_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 16 + b); };    // the Gram MMAs that read the numerators parked in b are done
   auto afull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };
   auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };
   auto eready_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 8 + g); };
@@ -368,8 +374,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull_bar, 1); mbar_init(tempty_bar, NUM_EPI_WARPS);
-    for (int b = 0; b < 2; ++b) { mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1); mbar_init(loaded_bar(b), NUM_EPI_WARPS); mbar_init(gfree_bar(b), 1);
+      mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS);
+    }
     for (int g = 0; g < IMGS; ++g) { mbar_init(eready_bar(g), 4); mbar_init(uready_bar(g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -430,9 +438,13 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     long long w_tempty = 0, w_full = 0; const long long t_begin = prof_on ? clock64() : 0;
     const uint64_t adesc0 = umma_desc_sw128(sbase + SMEM_STAGES);
     const uint64_t bdesc0 = umma_desc_sw128(sbase + SMEM_STAGES + A_BYTES);
-    const uint32_t tacc = tmem_base;
     for (ItemIter item(sched, first, step); DEBUG ? it == 0 : item.valid(); item.next(), ++it) {
-      mbar_wait_sleep_t(tempty_bar, (it & 1) ^ 1, w_tempty, prof_on);     // every epilogue warp has the previous tile in registers
+      // accumulator b = it & 1 is reusable once (a) every epilogue warp has item it-2 in registers and (b) the Gram MMAs
+      // of item it-2, which read the numerators parked in it, have completed.
+      const int ab = it & 1;
+      const uint32_t tacc = tmem_base + ab * ACC_PITCH;
+      mbar_wait_sleep_t(loaded_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
+      if (!DEBUG && !DUMP) mbar_wait_sleep_t(gfree_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
       tc_fence_after();
 #pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
@@ -447,7 +459,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
           umma_bf16(tacc, adesc + 4, bdesc + 4, IDESC, 1u);
           umma_bf16(tacc, adesc + 6, bdesc + 6, IDESC, 1u);
           umma_commit(empty_bar(stage));
-          if (kb == K_BLOCKS - 1) umma_commit(tfull_bar);
+          if (kb == K_BLOCKS - 1) umma_commit(tfull_bar(ab));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -473,7 +485,7 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
           if (n * IMGS + g >= p.n_img || (PROF && (p.skip_math & 1))) continue;
           mbar_wait_sleep(eready_bar(g), used[g]++ & 1);
           tc_fence_after();
-          const uint32_t te = tmem_base + PARK_BASE + g * PARK_PITCH;
+          const uint32_t te = tmem_base + b * ACC_PITCH + park_col(g);
           const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
           const uint64_t gdesc = umma_desc_nosw(aux + g * GRAM_BYTES, G_LBO, G_SBO);
           if (elect_one()) {
@@ -484,6 +496,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
           }
           __syncwarp();
         }
+        if (elect_one()) umma_commit(gfree_bar(b));      // every Gram MMA of this item done -> accumulator b may be overwritten
+        __syncwarp();
       }
     }
   } else {
@@ -517,11 +531,14 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t tu = tmem_base + U_BASE + g * GRAM_N + lane_sel;
-    const uint32_t tpark = tmem_base + PARK_BASE + g * PARK_PITCH + lane_sel;
+    const uint32_t tpark0 = tmem_base + park_col(g) + lane_sel;      // + ACC_PITCH for odd items
     float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
     uint32_t used = 0u;                         // completed phases of uready[g]
     long long w_tfull = 0, w_afull = 0, w_uready = 0; const long long t_begin = prof_on ? clock64() : 0;
     Carry c;
+    uint32_t hvp[18];                           // the carried item's numerators (fp16 pairs), as the tensor core saw them
+#pragma unroll
+    for (int k = 0; k < 18; ++k) hvp[k] = 0u;
     c.live = false; c.valid = false; c.P = c.D = c.wnorm = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
 
     auto phase_b = [&]() {
@@ -531,22 +548,22 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         const bool long_tile = (c.seg >> 16) & 1;
         mbar_wait_sleep_t(uready_bar(g), used++ & 1, w_uready, prof_on);
         tc_fence_after();
-        float U[R];
-        uint32_t hv[18];
-        TMEM_LD_X32(tu, U, 0);
-        TMEM_LD_X4(tu + 32, U, 32);
-        TMEM_LD_X16U(tpark, hv, 0);
-        TMEM_LD_X2U(tpark + 16, hv, 16);
-        float Zsum;
-        TMEM_LD_X1F(tu + 36, Zsum);              // ones column of the Gram pack: sum_k e_k
-        tmem_ld_wait();
-        // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form)
-        float q0 = 0.f, q1 = 0.f;
-        if (!(PROF && (p.skip_math & 16)))
+        // off-diagonal part of e^T G e with the fp16-rounded e the tensor core saw (symmetric form); U in two
+        // halves of 18 columns: the raw affinities of the NEXT item are already on their way into registers
+        float q0 = 0.f, q1 = 0.f, Zsum;
 #pragma unroll
-        for (int cidx = 0; cidx < 18; ++cidx) {
-          float2 ef = unpack_f16x2(hv[cidx]);
-          q0 = fmaf(ef.x, U[2 * cidx], q0); q1 = fmaf(ef.y, U[2 * cidx + 1], q1);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t Uh[18];
+          TMEM_LD_X16U(tu + 18 * h, Uh, 0);
+          TMEM_LD_X2U(tu + 18 * h + 16, Uh, 16);
+          if (h == 1) TMEM_LD_X1F(tu + 36, Zsum);            // ones column of the Gram pack: sum_k e_k
+          tmem_ld_wait();
+          if (!(PROF && (p.skip_math & 16)))
+#pragma unroll
+          for (int cidx = 0; cidx < 9; ++cidx) {
+            float2 ef = unpack_f16x2(hvp[9 * h + cidx]);
+            q0 = fmaf(ef.x, __uint_as_float(Uh[2 * cidx]), q0); q1 = fmaf(ef.y, __uint_as_float(Uh[2 * cidx + 1]), q1);
+          }
         }
         // e^T G e = sum e_k^2 (unit diagonal, fp32) + e^T (G - I) e (tensor core, fp16 operands)
         const float Qf = c.D + (q0 + q1);
@@ -599,16 +616,21 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
       const int img = n * IMGS + g;
       const bool valid = !DEBUG && !DUMP && img < p.n_img && !(PROF && (p.skip_math & 1));
 
-      // ---------------- phase A(t): raw affinities -> registers, accumulator handed back ---------
-      mbar_wait_sleep_t(tfull_bar, it & 1, w_tfull, prof_on);
+      // ---------------- raw affinities of item t on their way to registers ... ---------------------
+      const uint32_t tacc = tmem_base + b * ACC_PITCH + lane_sel;
+      mbar_wait_sleep_t(tfull_bar(b), (it >> 1) & 1, w_tfull, prof_on);
       tc_fence_after();
       float A[R];
-      TMEM_LD_X32(tmem_base + lane_sel + g * R, A, 0);
-      TMEM_LD_X4(tmem_base + lane_sel + g * R + 32, A, 32);
+      TMEM_LD_X32(tacc + g * R, A, 0);
+      TMEM_LD_X4(tacc + g * R + 32, A, 32);
+
+      // ---------------- ... while phase B(t-1) finishes the previous item (its Gram product has landed) ----
+      phase_b();
+
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive(loaded_bar(b));
       if (DEBUG) {
 #pragma unroll
         for (int k = 0; k < R; ++k) p.dump[(size_t)row * BLOCK_N + g * R + k] = A[k];
@@ -695,11 +717,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         }
       }
 
-      // ---------------- phase B(t-1): the previous item's Gram product has landed by now ----------
-      phase_b();
-
-      // ---------------- park(t): e(t) as fp16 (K padded 36 -> 48 with zeros), wake the Gram issuer --
+      // ---------------- park(t): e(t) as fp16 (K padded 36 -> 48 with zeros) in the group's own columns of the
+      // accumulator it came from, wake the Gram issuer; the same values stay in registers for phase B(t)
       if (valid) {
+        const uint32_t tpark = tpark0 + b * ACC_PITCH;
         uint32_t z[6] = {0u, 0u, 0u, 0u, 0u, 0u};
         TMEM_ST_X16(tpark, hv, 0);
         TMEM_ST_X2(tpark + 16, hv, 16);
@@ -710,6 +731,8 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(eready_bar(g));
       }
+#pragma unroll
+      for (int k = 0; k < 18; ++k) hvp[k] = hv[k];
       c.P = P; c.D = Dd; c.wnorm = wnorm; c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w;
       c.img = img; c.b = b; c.valid = valid; c.live = !DUMP;
     }
