@@ -23,16 +23,18 @@
 //   warp 2     TMEM allocator + issuer of the small "Gram" MMAs (see below)
 //   warp 3     aux loader: per-tile Gram packs, row metadata, word norms (bulk copies)
 //   warps 4-19 epilogue, four groups of four warps; group g owns image g of the tile and all 128 word
-//              rows (thread = one word row = one TMEM lane).  Per item:
-//                A(t)    tcgen05.ld the 36 raw affinities and hand the (single) accumulator straight back
-//                        to the MMA warp; leaky, l2norm over the caption's words (segmented warp scan),
+//              rows (thread = one word row = one TMEM lane).  Two accumulators alternate between items.  Per item:
+//                load    tcgen05.ld of the 36 raw affinities of item t is issued first, and while it is in flight
+//                B(t-1)  finishes the PREVIOUS item: tcgen05.ld U = e (G - I) (its Gram MMA completed long ago),
+//                        |ctx|^2 Z^2 = D + sum_k e_k U_k with e(t-1) still in registers, cosine, aggregation over
+//                        the caption's words, store;
+//                A(t)    leaky, l2norm over the caption's words (segmented warp scan),
 //                        e_k = exp2(lambda*ahat_k - lambda), P = sum e A, D = sum e^2;
-//                B(t-1)  finish the PREVIOUS item: tcgen05.ld U = e (G - I) and the parked fp16 e,
-//                        |ctx|^2 Z^2 = D + sum_k e_k U_k, cosine, aggregation over the caption's words, store;
-//                park(t) tcgen05.st e as fp16 into the group's TMEM parking area and wake the Gram issuer,
-//                        which runs U = e (G - I) as a 128x48x48 tcgen05.mma with A FROM TMEM and the
-//                        image's fp16 Gram pack as the SMEM B operand.
-//              The Gram product of item t therefore has a whole phase A to land: its latency is never exposed.
+//                park(t) tcgen05.st e as fp16 into 24 of the group's OWN 36 columns of the accumulator item t came
+//                        from (its values are in registers now) and wake the Gram issuer, which runs U = e (G - I)
+//                        as a 128x48x48 tcgen05.mma with A FROM TMEM and the image's fp16 Gram pack as the SMEM
+//                        B operand.  The MMA issuer reuses that accumulator for item t+2 once the Gram MMAs have
+//                        completed, so neither the accumulator hand-off nor the Gram latency is on the item cycle.
 //              The two cross-row reductions (l2norm over the caption's words, aggregation over words) are
 //              segmented warp scans -- itr_scan_plan_words guarantees a caption never straddles a warp,
 //              except in `long` tiles which exchange through shared memory.
@@ -71,9 +73,6 @@ constexpr int AUX_META = BLOCK_M * 16;             // 2048
 constexpr int AUX_WNORM = BLOCK_M * 4;             // 512
 constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 21568
 constexpr int XCH_FLOATS = 4 /*group*/ * 4 /*warp*/ * 40;
-// TMEM columns: [0,144) the accumulator (single buffer: it is released as soon as every epilogue
-// warp holds its 36 raw affinities in registers); [160,352) four 48-column Gram products U_g;
-// [352,472) four 24-column parking areas for the fp16 softmax numerators (32-column pitch).
 // Tensor memory (512 columns): two accumulators [0,144) and [144,288), four Gram products at 288 + 48 g.
 // The fp16 numerators e(t) of group g are parked INSIDE the accumulator the item came from, in 24 of the group's own
 // 36 columns (the group has its raw affinities in registers by then), so a second accumulator fits.
@@ -522,9 +521,10 @@ scan_t2i_tc_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_c
   } else {
     // =============================== epilogue =============================================
     // Group g (4 warps = all 128 word rows) owns image g of every tile.  Per item:
-    //   A(t)   load the 36 raw affinities (accumulator released right away), l2norm scan, exp
-    //   B(t-1) finish the PREVIOUS item: its Gram product landed during A(t)
-    //   park(t) write e(t) as fp16 to the group's TMEM parking area, signal the Gram issuer
+    //   load   issue the TMEM loads of the 36 raw affinities of item t
+    //   B(t-1) finish the PREVIOUS item while they are in flight (its Gram product landed long ago)
+    //   A(t)   l2norm scan, exp
+    //   park(t) write e(t) as fp16 into the group's own columns of the accumulator item t came from, signal the Gram issuer
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int g = (warp - EPI_WARP0) >> 2;      // epilogue group = image of the tile
