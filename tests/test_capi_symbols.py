@@ -94,3 +94,16 @@ def test_plan_words_packing_efficiency_coco_shape():
     n_tiles = check_plan(lens)
     eff = lens.sum() / (n_tiles * 128.0)
     assert eff > 0.94, eff            # share of MMA rows spent on real words (best-fit into 32-row quarters)
+
+
+def test_plan_words_fuzz():
+    """Property-based: any multiset of caption lengths in [1, 128] yields a valid plan (every caption exactly once,
+    whole captions inside one warp's 32 rows unless `long`, long captions alone in their tile)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=128), min_size=1, max_size=400))
+    def run(lens):
+        check_plan(lens)
+
+    run()
