@@ -431,6 +431,24 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": "first {} images x first {} captions of the same workload, fp32 torch CPU port of "
                                           "the reference's per-caption loop + numpy ranking, {:.1f} s".format(n_s, c_s, secs)}
+        # second, more relevant baseline: the reference's own op sequence -- one Python iteration
+        # per caption, repeat / bmm / softmax / bmm / cosine in float32 -- run in eager PyTorch on this same GPU, on a
+        # bounded sample of the workload (all images x the first captions); informational, the driver's ratio uses the CPU arm
+        try:
+            from oracle import ref_port
+            c_g = min(200, n_cap)
+            caps_g = captions_h[:c_g].to(dev)
+            ref_port.scan_scores(images, caps_g[:8], lengths[:8], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref_port.scan_scores(images, caps_g, lengths[:c_g], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            line["gpu_eager_baseline"] = {"value": n_img * c_g / dt, "unit": "pairs/s",
+                                          "sample": "all {} images x first {} captions, reference op sequence in eager PyTorch fp32 "
+                                                    "on the same GPU, {:.2f} s".format(n_img, c_g, dt)}
+        except Exception as exc:          # noqa: BLE001  (informational leg only)
+            line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:120]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
