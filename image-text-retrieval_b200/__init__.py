@@ -17,13 +17,14 @@ from . import synth                                            # noqa: F401
 from . import ops                                              # noqa: F401
 from .objectives import (ContrastiveLoss, MultiViewMatching, TripletLoss, cosine_sim, cosine_similarity,   # noqa: F401
                          func_attention, order_sim, xattn_score_i2t, xattn_score_t2i)
-from .evaluation import cal_recall, cal_sims, cal_sims_and_recall, device_ranks, device_sims, encode_data, i2t, t2i    # noqa: F401
+from .evaluation import (cal_recall, cal_sims, cal_sims_and_recall, cal_sims_and_recall_ensemble, device_ranks,   # noqa: F401
+                         device_sims, encode_data, i2t, t2i)
 from . import sharding                                         # noqa: F401
 
 OBJECTIVES_SYMBOLS = ("cosine_sim", "order_sim", "cosine_similarity", "xattn_score_t2i", "xattn_score_i2t", "func_attention",
                       "ContrastiveLoss", "TripletLoss")
 FUSION_SYMBOLS = ("MultiViewMatching",)
-EVALUATION_SYMBOLS = ("encode_data", "cal_sims", "i2t", "t2i", "cal_recall", "cal_sims_and_recall")
+EVALUATION_SYMBOLS = ("encode_data", "cal_sims", "i2t", "t2i", "cal_recall", "cal_sims_and_recall", "cal_sims_and_recall_ensemble")
 
 
 def _fusion_module():
@@ -79,7 +80,7 @@ def uninstall(objectives_module=None, evaluation_module=None, fusion_module=None
             continue
         for name, fn in getattr(mod, "_itr_b200_orig", {}).items():
             setattr(mod, name, fn)
-        for name in ("cal_sims_and_recall",):
+        for name in ("cal_sims_and_recall", "cal_sims_and_recall_ensemble"):
             if hasattr(mod, name) and name not in getattr(mod, "_itr_b200_orig", {}):
                 delattr(mod, name)
         if hasattr(mod, "_itr_b200_orig"):

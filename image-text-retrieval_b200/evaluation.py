@@ -264,3 +264,24 @@ def cal_sims_and_recall(model, img_embs, cap_embs, lengths=None, shard_size=128,
     if return_sims:
         res["sims"] = sims
     return res
+
+
+def cal_sims_and_recall_ensemble(models, img_embs_list, cap_embs_list, lengths_list=None, shard_size=128,
+                                 return_sims=False, verbose=False):
+    """Two-model (or n-model) ensemble of ``evalrank_ensemble`` (evaluation.py:378-401): the models' score matrices are
+    averaged and ranked on the device, (s1 + s2) / 2 in float32 exactly as the reference's numpy average of the
+    float32 blocks; nothing but the rank vectors comes back."""
+    if not (len(models) == len(img_embs_list) == len(cap_embs_list)) or not models:
+        raise ValueError("models, img_embs_list and cap_embs_list must be equally long and non-empty")
+    lengths_list = lengths_list if lengths_list is not None else [None] * len(models)
+    sims = None
+    for model, img, cap, ln in zip(models, img_embs_list, cap_embs_list, lengths_list):
+        s = device_sims(model, img, cap, ln, shard_size)
+        sims = s if sims is None else sims.add_(s)
+    if len(models) > 1:
+        sims = sims.mul_(1.0 / len(models))
+    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in device_ranks(sims)]
+    res = _recall_dict(_metrics(a), (a, b), _metrics(c), (c, d), verbose)
+    if return_sims:
+        res["sims"] = sims
+    return res

@@ -308,3 +308,27 @@ def test_empty_inputs_return_empty_matrices():
     assert tuple(itr_b200.MultiViewMatching()(torch.zeros(0, 12, 64, device="cuda"), torch.rand(5, 64, device="cuda")).shape) == (0, 5)
     d_im, d_cap = ops.scan_backward_f32(z_im, cap, [7, 3], torch.zeros(0, 2, device="cuda"), "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
     assert tuple(d_im.shape) == (0, 36, 1024) and not d_cap.any()
+
+
+def test_ensemble_of_two_models_matches_averaged_matrices():
+    """evalrank_ensemble (evaluation.py:378-401): (sims_1 + sims_2) / 2 then cal_recall -- here averaged and ranked on
+    the device; one VSE++ model and one SCAN model on the same 40 x 200 split."""
+    import types
+    rng = np.random.default_rng(3)
+    n, d = 40, 64
+    im = rng.standard_normal((n, d)); im /= np.linalg.norm(im, axis=1, keepdims=True)
+    s = np.repeat(im, 5, axis=0) + 0.7 * rng.standard_normal((5 * n, d)); s /= np.linalg.norm(s, axis=1, keepdims=True)
+    img2, cap2, ln2 = itr_b200.synth.scan_inputs(n, 5 * n, 10.5, 9)
+    m1 = types.SimpleNamespace(config=dict(name="VSE++"), sim_enc=None)
+    m1.criterion = ob.ContrastiveLoss(m1.config, 0.2, "cosine", True)
+    m2 = types.SimpleNamespace(config=cfg(), sim_enc=None)
+    m2.criterion = ob.ContrastiveLoss(m2.config, 0.2, "cosine", True)
+    res = ev.cal_sims_and_recall_ensemble([m1, m2], [im.astype(np.float32), img2.numpy()], [s.astype(np.float32), cap2.numpy()],
+                                          [None, ln2], return_sims=True)
+    s1 = ev.cal_sims(m1, im.astype(np.float32), s.astype(np.float32))
+    s2 = ev.cal_sims(m2, img2.numpy(), cap2.numpy(), ln2)
+    want = so.recall_dict((s1.astype(np.float32) + s2.astype(np.float32)) / 2)
+    np.testing.assert_allclose(res["sims"].cpu().numpy(), (s1 + s2) / 2, rtol=1e-6, atol=1e-7)
+    assert res["rsum"] == pytest.approx(want["rsum"]) and res["i2t_r1"] == pytest.approx(want["i2t_r1"])
+    np.testing.assert_array_equal(res["t2i_ranks"], want["t2i_ranks"])
+    np.testing.assert_array_equal(res["i2t_ranks"], want["i2t_ranks"])
