@@ -16,12 +16,12 @@ from . import _capi as capi                                    # noqa: F401  (ct
 from . import synth                                            # noqa: F401
 from . import ops                                              # noqa: F401
 from .objectives import (ContrastiveLoss, MultiViewMatching, TripletLoss, cosine_sim, cosine_similarity,   # noqa: F401
-                         func_attention, order_sim, xattn_score_i2t, xattn_score_t2i)
+                         func_attention, order_sim, pdist, pdist_cos, xattn_score_i2t, xattn_score_t2i)
 from .evaluation import (cal_recall, cal_sims, cal_sims_and_recall, cal_sims_and_recall_ensemble, device_ranks,   # noqa: F401
                          device_sims, encode_data, i2t, t2i)
 from . import sharding                                         # noqa: F401
 
-OBJECTIVES_SYMBOLS = ("cosine_sim", "order_sim", "cosine_similarity", "xattn_score_t2i", "xattn_score_i2t", "func_attention",
+OBJECTIVES_SYMBOLS = ("cosine_sim", "order_sim", "pdist", "pdist_cos", "cosine_similarity", "xattn_score_t2i", "xattn_score_i2t", "func_attention",
                       "ContrastiveLoss", "TripletLoss")
 FUSION_SYMBOLS = ("MultiViewMatching",)
 EVALUATION_SYMBOLS = ("encode_data", "cal_sims", "i2t", "t2i", "cal_recall", "cal_sims_and_recall", "cal_sims_and_recall_ensemble")

@@ -88,6 +88,23 @@ class _CosineScores(torch.autograd.Function):
         return d_im, d_s
 
 
+def pdist(x1, x2, *args):
+    """Objectives.py:296-306 (SAEM): pairwise Euclidean distance sqrt(|x1|^2 - 2 x1.x2 + |x2|^2 + 1e-4); the
+    (h1, h2) contraction is the native GEMM, the rank-1 terms are elementwise."""
+    x1_square = torch.sum(x1 * x1, 1).view(-1, 1)
+    x2_square = torch.sum(x2 * x2, 1).view(1, -1)
+    return torch.sqrt(x1_square - 2 * cosine_sim(x1, x2) + x2_square + 1e-4)
+
+
+def pdist_cos(x1, x2, *args):
+    """Objectives.py:309-323 (SAEM): cosine similarity of un-normalised rows; zero rows give 0 (the reference
+    zeroes the NaNs of 0/0)."""
+    x1_norm = x1 / x1.norm(dim=1)[:, None]
+    x2_norm = x2 / x2.norm(dim=1)[:, None]
+    res = cosine_sim(torch.nan_to_num(x1_norm, nan=0.0), torch.nan_to_num(x2_norm, nan=0.0))
+    return res
+
+
 class _OrderScores(torch.autograd.Function):
     @staticmethod
     def forward(ctx, im, s):
@@ -245,9 +262,7 @@ class ContrastiveLoss(nn.Module):
             raise ValueError("unknown measure:", measure)
         name = self.config["name"]
         if name == "SAEM":
-            # SAEM's pdist similarities are outside the accelerated path
-            from itr.modalmodule import Objectives as _ref   # the reference package this drop-in is installed into
-            self.sim = _ref.pdist if measure == "order" else _ref.pdist_cos
+            self.sim = pdist if measure == "order" else pdist_cos       # Objectives.py:52-60
         elif name == "SCAN":
             if self.config["cross_attn"] == "t2i":
                 self.sim = xattn_score_t2i

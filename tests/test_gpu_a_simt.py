@@ -332,3 +332,25 @@ def test_ensemble_of_two_models_matches_averaged_matrices():
     assert res["rsum"] == pytest.approx(want["rsum"]) and res["i2t_r1"] == pytest.approx(want["i2t_r1"])
     np.testing.assert_array_equal(res["t2i_ranks"], want["t2i_ranks"])
     np.testing.assert_array_equal(res["i2t_ranks"], want["i2t_ranks"])
+
+
+def test_saem_pdist_measures():
+    """SAEM's pdist / pdist_cos (Objectives.py:296-323) over the native GEMM, with autograd, against plain torch."""
+    g = torch.Generator().manual_seed(8)
+    x1 = torch.randn(17, 96, generator=g).cuda().requires_grad_(True)
+    x2 = torch.randn(23, 96, generator=g).cuda().requires_grad_(True)
+    a, b = x1.detach().clone().requires_grad_(True), x2.detach().clone().requires_grad_(True)
+    w = torch.randn(17, 23, generator=g).cuda()
+    for ours, ref in ((ob.pdist, lambda p, q: torch.sqrt((p * p).sum(1).view(-1, 1) - 2 * p.mm(q.t()) + (q * q).sum(1).view(1, -1) + 1e-4)),
+                      (ob.pdist_cos, lambda p, q: (p / p.norm(dim=1)[:, None]).mm((q / q.norm(dim=1)[:, None]).t()))):
+        for t in (x1, x2, a, b):
+            t.grad = None
+        got, want = ours(x1, x2), ref(a, b)
+        np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=2e-6)
+        (got * w).sum().backward(); (want * w).sum().backward()
+        np.testing.assert_allclose(x1.grad.cpu().numpy(), a.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(x2.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    z = torch.zeros(2, 96, device="cuda")
+    assert torch.equal(ob.pdist_cos(z, x2.detach()), torch.zeros(2, 23, device="cuda"))     # the reference zeroes 0/0
+    crit = ob.ContrastiveLoss(dict(name="SAEM"), margin=0.2, measure="cosine", max_violation=True)
+    assert crit.sim is ob.pdist_cos
