@@ -73,12 +73,12 @@ def test_metrics_formula():
 
 def test_install_and_uninstall_on_standin_modules():
     O = types.ModuleType("Objectives"); E = types.ModuleType("evaluation")
-    O.cosine_sim = "orig_cos"; O.ContrastiveLoss = "orig_loss"; O.pdist = "keep"
+    O.cosine_sim = "orig_cos"; O.ContrastiveLoss = "orig_loss"; O.l1norm_d = "keep"; O.pdist = "orig_pdist"
     E.cal_sims = "orig_cal"; E.i2t = "orig_i2t"; E.encode_data = "keep"
     itr_b200.install(O, E)
     assert O.cosine_sim is ob.cosine_sim and O.ContrastiveLoss is ob.ContrastiveLoss and O.xattn_score_t2i is ob.xattn_score_t2i
     assert E.cal_sims is ev.cal_sims and E.i2t is ev.i2t and E.cal_recall is ev.cal_recall and E.encode_data is ev.encode_data
-    assert O.pdist == "keep" and E._itr_b200_orig["encode_data"] == "keep"
+    assert O.l1norm_d == "keep" and O.pdist is ob.pdist and E._itr_b200_orig["encode_data"] == "keep"
     itr_b200.install(O, E)       # idempotent: originals are not overwritten by the patched ones
     assert O._itr_b200_orig["cosine_sim"] == "orig_cos"
     itr_b200.uninstall(O, E)
