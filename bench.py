@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the oracle port of the reference's op sequence in eager PyTorch on the GPU (informational)")
     ap.add_argument("--n-img", type=int, default=5000, help="override for debugging only (invalidates the number)")
     ap.add_argument("--n-cap", type=int, default=25000)
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5, 6],
@@ -431,9 +433,10 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": "first {} images x first {} captions of the same workload, fp32 torch CPU port of "
                                           "the reference's per-caption loop + numpy ranking, {:.1f} s".format(n_s, c_s, secs)}
-        # second, more relevant baseline: the reference's own op sequence -- one Python iteration
-        # per caption, repeat / bmm / softmax / bmm / cosine in float32 -- run in eager PyTorch on this same GPU, on a
-        # bounded sample of the workload (all images x the first captions); informational, the driver's ratio uses the CPU arm
+    # optional second baseline (--gpu-eager-baseline): the reference's own op sequence -- one Python
+    # iteration per caption, repeat / bmm / softmax / bmm / cosine in float32 -- in eager PyTorch on this same GPU, on a
+    # bounded sample of the workload (all images x the first captions); informational, the driver's ratio uses the CPU arm
+    if world == 1 and args.gpu_eager_baseline:
         try:
             from oracle import ref_port
             c_g = min(200, n_cap)
