@@ -31,6 +31,24 @@ def _precision(config):
     return mode
 
 
+def _train_precision(config):
+    """Forward precision under autograd: "fp32" (default: the loss matches the reference to 1e-5) or "bf16" (config key
+    ``itr_b200_train_precision`` / env ``ITR_B200_TRAIN_PRECISION``): t2i scores from the fused tensor-core kernel,
+    within 1e-3; the backward is the float32 closed form either way."""
+    mode = None
+    if isinstance(config, dict):
+        mode = config.get("itr_b200_train_precision")
+    mode = mode or os.environ.get("ITR_B200_TRAIN_PRECISION") or "fp32"
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("itr_b200_train_precision must be 'bf16' or 'fp32', got {!r}".format(mode))
+    return mode
+
+
+def capi_max_words():
+    from . import _capi
+    return _capi.MAX_WORDS_F32          # the float32 backward bounds the caption length under autograd
+
+
 def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
@@ -41,9 +59,13 @@ class _ScanScores(torch.autograd.Function):
     (``itr_scan_backward_f32``) -- nothing but the inputs is kept between the two."""
 
     @staticmethod
-    def forward(ctx, images, captions, lens, cross_attn, norm, agg, lam_sm, lam_lse):
+    def forward(ctx, images, captions, lens, cross_attn, norm, agg, lam_sm, lam_lse, tc_forward=False):
         ctx.save_for_backward(images, captions)
         ctx.args = (lens, cross_attn, norm, agg, lam_sm, lam_lse)
+        if tc_forward:      # opt-in: scores from the fused tensor-core kernel (bf16 inputs); the backward stays float32
+            pi = ops.prepare_images(images.detach())
+            pc = ops.prepare_captions(captions.detach().contiguous(), lens)
+            return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, lam_sm, lam_lse)
         return ops.scan_scores_f32(images, captions, lens, cross_attn, norm, agg, lam_sm, lam_lse)
 
     @staticmethod
@@ -52,7 +74,7 @@ class _ScanScores(torch.autograd.Function):
         lens, cross_attn, norm, agg, lam_sm, lam_lse = ctx.args
         d_im, d_cap = ops.scan_backward_f32(images, captions, lens, g, cross_attn, norm, agg, lam_sm, lam_lse)
         return (d_im.to(images.dtype) if ctx.needs_input_grad[0] else None,
-                d_cap.to(captions.dtype) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)
+                d_cap.to(captions.dtype) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -164,7 +186,9 @@ def _scan(images, captions, cap_lens, config, cross_attn):
         return torch.zeros(images.size(0), captions.size(0), device=images.device, dtype=torch.float32)
     if _needs_grad(images, captions):
         ln = ops.lengths_to_numpy(cap_lens, captions.size(0))
-        return _ScanScores.apply(images, captions, ln, cross_attn, norm, agg, float(lam_sm), float(lam_lse))
+        tc = (_train_precision(config) == "bf16" and cross_attn == "t2i" and norm in ("clipped_l2norm", "l2norm")
+              and ops.tc_shapes(images, captions) and 1 <= ln.min(initial=1) and ln.max(initial=0) <= capi_max_words())
+        return _ScanScores.apply(images, captions, ln, cross_attn, norm, agg, float(lam_sm), float(lam_lse), tc)
     images, captions = images.detach(), captions.detach()
     if _precision(config) == "bf16" and ops.tc_shapes(images, captions) and norm in ("clipped_l2norm", "l2norm", "softmax", "clipped", "no_norm"):
         ln = ops.lengths_to_numpy(cap_lens, captions.size(0))

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from conftest import bits_to_f32, load_golden
+import itr_b200
 from itr_b200 import objectives as ob, ops
 from oracle import scan_backward as sb, scan_oracle as so
 
@@ -168,3 +169,23 @@ def test_other_region_counts_and_embed_sizes(direction, lam_sm, n_regions, d):
     (scores * torch.from_numpy(dS).cuda()).sum().backward()
     close(img.grad, want_im, msg="d_images")
     close(cap.grad, want_cap, msg="d_captions")
+
+
+def test_training_forward_on_tensor_cores_is_opt_in():
+    """itr_b200_train_precision="bf16": the scores under autograd come from the fused tcgen05 kernel (within 1e-3 of the
+    float32 ones), the gradients are the same float32 closed form."""
+    img, cap, ln = itr_b200.synth.scan_inputs(12, 12, 10.5, 23, device="cuda", lengths=np.array([5, 9, 14, 3, 22, 7, 11, 30, 4, 16, 8, 12]))
+    out = {}
+    for mode in ("fp32", "bf16"):
+        a, b = img.clone().requires_grad_(True), cap.clone().requires_grad_(True)
+        crit = ob.ContrastiveLoss(cfg(itr_b200_train_precision=mode, max_violation=False), margin=0.2, measure="cosine", max_violation=False)
+        loss = crit(a, b, ln.tolist())
+        loss.backward()
+        out[mode] = (loss.item(), a.grad.clone(), b.grad.clone())
+    assert abs(out["bf16"][0] - out["fp32"][0]) <= 2e-3 * abs(out["fp32"][0])
+    assert out["bf16"][0] != out["fp32"][0]                       # it really took the other forward
+    for k in (1, 2):                                              # sum hinge: same active set up to near-ties -> close gradients
+        scale = out["fp32"][k].abs().max().item()
+        assert (out["bf16"][k] - out["fp32"][k]).abs().max().item() <= 0.05 * scale
+    with pytest.raises(ValueError):
+        ob.xattn_score_t2i(img.clone().requires_grad_(True), cap, ln, cfg(itr_b200_train_precision="fp8"))
