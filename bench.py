@@ -13,7 +13,9 @@ sharded across ranks (strong scaling: the total problem is fixed).
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the
 same metric through the public API (itr_b200.sharding.sharded_scan_eval, the multi-GPU form of
-cal_sims + cal_recall) with pinned HOST buffers, copies inside the timed region.
+cal_sims + cal_recall) with pinned HOST buffers, copies inside the timed region; `e2e_dropin` (N = 1) is
+the reference's own call sequence through the drop-in symbols -- cal_sims(numpy inputs) -> float64 host
+matrix -> cal_recall(sims) -- and `device_breakdown_ms` splits the device step into its four stages.
 """
 from __future__ import annotations
 
@@ -54,15 +56,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gpu-eager-baseline", action="store_true",
-                    help="also time the oracle port of the reference's op sequence in eager PyTorch on the GPU (informational)")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true",
+                    help="skip the same-GPU baseline (the reference's op sequence in eager PyTorch on this GPU, ~0.5 s sample)")
     ap.add_argument("--n-img", type=int, default=5000, help="override for debugging only (invalidates the number)")
     ap.add_argument("--n-cap", type=int, default=25000)
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5, 6],
                     help="BASELINE.json config to measure; 5 (default) is the headline the driver runs; "
                          "6 = SCAN training step (fwd + bwd, batch 128), not a BASELINE config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-caps", type=int, default=300)
+    ap.add_argument("--cpu-sample-caps", type=int, default=CPU_SAMPLE[1])
     return ap.parse_args()
 
 
@@ -118,55 +120,79 @@ class ClockSampler:
 
 
 _CPU_INPUTS = {}
+CPU_SAMPLE = (1000, 100)      # images x captions of the COCO-5K-shaped workload scored per CPU step (both CPU legs)
 
 
-def cpu_port_rate(n_img_s, n_cap_s, seed=14, lam=10.5, repeats=1):
-    """The oracle's float32 torch-CPU port (same per-caption loop as the reference) on a bounded
-    sample of the workload: first n_img_s images x first n_cap_s captions.  Returns (pairs/s, seconds, cores)."""
+def _reference_fns():
+    """(kind, scan_t2i(img, cap, lens) -> (n_img, n_cap) tensor, i2t, t2i): the reference's own functions when its
+    package is importable (oracle/_ref on the GPU box, /root/reference in the authoring container), else the port."""
+    from oracle import ref_loader, ref_port
+    if ref_loader.available():
+        try:
+            O, E = ref_loader.load()
+            cfg = dict(CONFIG)
+            return ("reference", lambda img, cap, ln: O.xattn_score_t2i(img, cap, [int(x) for x in ln], cfg),
+                    lambda s: E.i2t(s), lambda s: E.t2i(s))
+        except Exception:      # noqa: BLE001  (a missing third-party import of the reference: fall back to the port)
+            pass
+    return ("port", lambda img, cap, ln: ref_port.scan_scores(img, cap, ln, "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0),
+            ref_port.i2t_ranks, ref_port.t2i_ranks)
+
+
+def cpu_reference_rate(n_img_s, n_cap_s, seed=14, lam=10.5, repeats=1):
+    """The reference's CPU path (float32 torch, one Python iteration per caption, then numpy argsort ranking) on a
+    bounded sample of the workload: first n_img_s images x first n_cap_s captions.
+    Returns (pairs/s, seconds, cores, kind)."""
     from itr_b200 import synth
-    from oracle import ref_port
     if (n_img_s, n_cap_s) not in _CPU_INPUTS:
         lengths = synth.caption_lengths(25000, lam, seed)[:n_cap_s]
         _CPU_INPUTS[(n_img_s, n_cap_s)] = synth.scan_inputs(n_img_s, n_cap_s, lam, seed, device="cpu", lengths=lengths)
     img, cap, ln = _CPU_INPUTS[(n_img_s, n_cap_s)]
+    kind, scan, i2t, t2i = _reference_fns()
     cores = torch.get_num_threads()
-    ref_port.scan_scores(img[:8], cap[:4], ln[:4], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)   # warm-up
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        s = ref_port.scan_scores(img, cap, ln, "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
-        sims = s.double().numpy()
-        # the reference then ranks on the host; time it on the sample's square part
-        m = min(n_img_s, n_cap_s // 5)
-        if m >= 1:
-            ref_port.i2t_ranks(sims[:m, : 5 * m]); ref_port.t2i_ranks(sims[:m, : 5 * m])
-        best = min(best, time.perf_counter() - t0)
-    return n_img_s * n_cap_s / best, best, cores
+    with torch.no_grad():
+        scan(img[:8], cap[:4], ln[:4])   # warm-up
+        best = float("inf")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            sims = scan(img, cap, ln).double().numpy()
+            # the reference then ranks on the host; time it on the sample's square part
+            m = min(n_img_s, n_cap_s // 5)
+            if m >= 1:
+                i2t(sims[:m, : 5 * m]); t2i(sims[:m, : 5 * m])
+            best = min(best, time.perf_counter() - t0)
+    return n_img_s * n_cap_s / best, best, cores, kind
+
+
+def _cpu_sample_text(n_img_s, n_cap_s, kind, secs=None):
+    what = "the reference's own xattn_score_t2i + i2t/t2i (oracle/_ref, unmodified)" if kind == "reference" else \
+        "the oracle's float32 torch port of the reference's per-caption loop + numpy ranking"
+    return "first {} images x first {} captions of the COCO-5K-shaped workload per step, {} on the host cores{}".format(
+        n_img_s, n_cap_s, what, "" if secs is None else ", {:.1f} s".format(secs))
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; /root/reference is absent on the GPU
-    box and is pure Python, so there is nothing to compile) on this box's host cores."""
+    """--impl reference: the reference's CPU path on this box's host cores (the reference package staged under
+    oracle/_ref when present, else the oracle port), same sample as the `cpu_baseline` leg of the b200 arm."""
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    n_img_s, n_cap_s = min(1000, args.n_img), min(args.cpu_sample_caps // 3, args.n_cap)
+    n_img_s, n_cap_s = min(CPU_SAMPLE[0], args.n_img), min(CPU_SAMPLE[1], args.n_cap)
     times = []
     for i in range(args.warmup + args.steps):
-        rate, secs, cores = cpu_port_rate(n_img_s, n_cap_s)
+        rate, secs, cores, kind = cpu_reference_rate(n_img_s, n_cap_s)
         if i >= args.warmup:
             times.append(secs)
-        if i == 0 and secs * (args.warmup + args.steps) > 240:      # keep the whole run within minutes
-            n_cap_s = max(10, int(n_cap_s * 240 / (secs * (args.warmup + args.steps))))
     t = float(np.mean(times))
     value = n_img_s * n_cap_s / t
-    sample = "first {} images x first {} captions of the COCO-5K-shaped workload per step, fp32 torch CPU".format(n_img_s, n_cap_s)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SCAN t2i LSE COCO-5K shape (5000 img x 25000 caps); CPU arm scores a bounded sample per step",
+            "config": {"workload": "SCAN t2i LSE COCO-5K shape (5000 img x 25000 caps); the CPU arm scores a bounded sample per step "
+                                   "and reports the rate",
                        "n_img": args.n_img, "n_cap": args.n_cap},
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
+                             "sample": _cpu_sample_text(n_img_s, n_cap_s, kind)},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -280,7 +306,7 @@ def run_side_config(args):
                 tot_ms32 += _time_cuda(lambda: dev_step(dict(cfg, itr_b200_precision="fp32")), 1, warmup=1)
             r = [x.cpu().numpy().astype(np.float64) for x in dev_step()]
             rsums.append(sum(100.0 * np.mean(r[0] < k) + 100.0 * np.mean(r[2] < k) for k in (1, 5, 10)))
-        n_s, c_s = 1000, max(20, args.cpu_sample_caps // 3)
+        n_s, c_s = 1000, max(20, args.cpu_sample_caps)
         t0 = time.perf_counter()
         ref_port.scan_scores(img[:n_s].cpu(), cap[:c_s].cpu(), ln[:c_s], direction, "clipped_l2norm", agg, lam, 6.0)
         cpu_rate = n_s * c_s / (time.perf_counter() - t0)
@@ -332,19 +358,22 @@ def main():
     torch.cuda.synchronize()
 
     scores = torch.empty(n_img, hi - lo, device=dev, dtype=torch.float32)
-    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k_end = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # per-step device breakdown: [start, images prepared (+ all-gathered), captions packed, scores done, ranks merged]
+    marks = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
 
     def step(i=None):
+        mark = (lambda k: marks[i][k].record()) if i is not None else (lambda k: None)
+        mark(0)
         pi = ops.prepare_images_sharded(images, None, dev)      # each rank preps 1/N of the images + NCCL all-gather
+        mark(1)
         pc = ops.prepare_captions(captions, ln_local)
-        if i is not None:
-            k_start[i].record()
+        mark(2)
         ops.scan_t2i_scores_bf16(pi, pc, CONFIG["raw_feature_norm"], CONFIG["agg_func"], CONFIG["lambda_softmax"],
                                  CONFIG["lambda_lse"], out=scores)
-        if i is not None:
-            k_end[i].record()
-        return sharding.sharded_ranks(scores, lo, n_cap, None, 5)
+        mark(3)
+        out = sharding.sharded_ranks(scores, lo, n_cap, None, 5)
+        mark(4)
+        return out
 
     for _ in range(args.warmup):
         out = step()
@@ -360,10 +389,15 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    kern_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in zip(k_start, k_end)]))], device=dev)
+    seg = [float(np.mean([m[k].elapsed_time(m[k + 1]) for m in marks])) for k in range(4)]
+    kern_ms = torch.tensor([seg[2]], device=dev)
+    seg_ms = torch.tensor(seg, device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(seg_ms, op=dist.ReduceOp.MAX)
+    breakdown = dict(zip(["prep_images" + ("+all_gather" if world > 1 else ""), "pack_captions", "score_kernel",
+                          "rank_kernels" + ("+exchange" if world > 1 else "")], [round(x, 3) for x in seg_ms.tolist()]))
     ms_per_step = elapsed_ms.item() / args.steps
     value = n_img * n_cap / (ms_per_step * 1e-3)
     i2t_ranks, _, t2i_ranks, _ = out
@@ -390,6 +424,48 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_img * n_cap / e2e_s.item()
+
+    # ------------------------------------------------------------------ the reference's own call sequence (N = 1)
+    # evalrank_single (evaluation.py:284-291) / validate_step (utils.py:152-167): numpy inputs -- the image array is the
+    # PAGEABLE copy the reference's de-duplication makes, the captions are what encode_data returned -- then
+    # sims = cal_sims(...) (host float64 matrix) and cal_recall(sims) / i2t(sims) + t2i(sims).
+    dropin = None
+    if world == 1:
+        class _M:
+            sim_enc = None
+        from itr_b200.objectives import ContrastiveLoss
+        model = _M(); model.config = CONFIG
+        model.criterion = ContrastiveLoss(CONFIG, margin=0.2, measure="cosine", max_violation=True)
+        imgs_np = np.array(images_h.numpy())                       # pageable, like numpy.array([img_embs[i] ...])
+        caps_np = captions_h.numpy()                               # view of the pinned buffer encode_data fills
+        import contextlib, io
+
+        def dropin_step(validate=False):
+            with contextlib.redirect_stdout(io.StringIO()):
+                sims = ev.cal_sims(model, imgs_np, caps_np, lengths=ln_local, shard_size=640)
+                if validate:
+                    return sims, (ev.i2t(sims), ev.t2i(sims))
+                return sims, ev.cal_recall(sims)
+
+        for _ in range(2):
+            sims_h, res_d = dropin_step()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            sims_h, res_d = dropin_step()
+        torch.cuda.synchronize()
+        dropin_s = (time.perf_counter() - w0) / args.steps
+        w0 = time.perf_counter()
+        sims_h, (r_i, r_t) = dropin_step(validate=True)
+        validate_s = time.perf_counter() - w0
+        dropin = {"value": n_img * n_cap / dropin_s, "unit": "pairs/s", "ms_per_step": dropin_s * 1e3,
+                  "ms_per_step_validate_sequence": validate_s * 1e3,
+                  "vs_e2e": dropin_s / e2e_s.item(), "rsum": res_d["rsum"],
+                  "sims": "{} {} host matrix returned by cal_sims".format(sims_h.dtype, tuple(sims_h.shape)),
+                  "call": "cal_sims(model, pageable numpy images, numpy captions, lengths) -> float64 host matrix; cal_recall(sims)",
+                  "h2d_bytes_per_step": n_img * R * D * 4 + sum_words_local * D * 4,
+                  "d2h_bytes_per_step": n_img * n_cap * 8 + (n_img * 2 + n_cap * 2) * 8}
+        del sims_h, imgs_np
     n_tiles = ops.plan_words(ln_local)[1]
     h2d = -(-n_img // world) * R * D * 4 + sum_words_local * D * 4 + n_tiles * 128 * 16
     d2h = (n_img * 2 + n_cap * 2) * 8
@@ -413,6 +489,7 @@ def main():
                        (n_img * R * D * 2 + n_tiles * 128 * D * 2) / 1e6, n_img * (hi - lo) * 4 / 1e6),
                    "step": "prep(cast,pack,gram" + (", image shards all-gathered over NCCL" if world > 1 else "") + ") + tcgen05 scores + rank kernels" + (" + rank exchange" if world > 1 else "")},
         "eval_wall_ms": {"device": ms_per_step, "e2e": e2e_s.item() * 1e3},
+        "device_breakdown_ms": breakdown,
         "recall_check": {"i2t_r1": r1, "t2i_r1": r1_t, "e2e_rsum": res["rsum"]},
         "roofline": {"bound": "tensor", "kernel": "scan_t2i_tc_kernel", "achieved": achieved, "peak": pk["tflops"],
                      "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": measured_traffic(n_img, n_cap, world),
@@ -426,30 +503,32 @@ def main():
         "gpu_launches": 5 * args.steps,
         "clocks": clocks,
     }
+    if dropin is not None:
+        line["e2e_dropin"] = dropin
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        n_s, c_s = min(1000, n_img), min(args.cpu_sample_caps, n_cap)
-        rate, secs, cores = cpu_port_rate(n_s, c_s)
-        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": "first {} images x first {} captions of the same workload, fp32 torch CPU port of "
-                                          "the reference's per-caption loop + numpy ranking, {:.1f} s".format(n_s, c_s, secs)}
-    # optional second baseline (--gpu-eager-baseline): the reference's own op sequence -- one Python
-    # iteration per caption, repeat / bmm / softmax / bmm / cosine in float32 -- in eager PyTorch on this same GPU, on a
-    # bounded sample of the workload (all images x the first captions); informational, the driver's ratio uses the CPU arm
-    if world == 1 and args.gpu_eager_baseline:
+        n_s, c_s = min(CPU_SAMPLE[0], n_img), min(args.cpu_sample_caps, n_cap)
+        rate, secs, cores, kind = cpu_reference_rate(n_s, c_s)
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
+                                "sample": _cpu_sample_text(n_s, c_s, kind, secs)}
+    # second baseline: the reference's own op sequence -- one Python iteration per caption,
+    # repeat / bmm / softmax / bmm / cosine in float32 -- in eager PyTorch on this same GPU, on a bounded sample of the
+    # workload (all images x the first captions, ~0.5 s); informational, the driver's ratio uses the CPU arm
+    if world == 1 and not args.no_gpu_eager_baseline:
         try:
-            from oracle import ref_port
-            c_g = min(200, n_cap)
+            kind, scan, _, _ = _reference_fns()
+            c_g = min(60, n_cap)
             caps_g = captions_h[:c_g].to(dev)
-            ref_port.scan_scores(images, caps_g[:8], lengths[:8], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            ref_port.scan_scores(images, caps_g, lengths[:c_g], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
-            torch.cuda.synchronize()
+            with torch.no_grad():
+                scan(images, caps_g[:8], lengths[:8])
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                scan(images, caps_g, lengths[:c_g])
+                torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            line["gpu_eager_baseline"] = {"value": n_img * c_g / dt, "unit": "pairs/s",
-                                          "sample": "all {} images x first {} captions, reference op sequence in eager PyTorch fp32 "
-                                                    "on the same GPU, {:.2f} s".format(n_img, c_g, dt)}
+            line["gpu_eager_baseline"] = {"value": n_img * c_g / dt, "unit": "pairs/s", "kind": kind,
+                                          "sample": "all {} images x first {} captions, the reference's xattn_score_t2i op sequence in "
+                                                    "eager PyTorch fp32 on the same GPU, {:.2f} s".format(n_img, c_g, dt)}
         except Exception as exc:          # noqa: BLE001  (informational leg only)
             line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:120]}
     print(json.dumps(line), flush=True)

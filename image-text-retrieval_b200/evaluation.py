@@ -16,7 +16,10 @@ Differences from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import os
+import threading
 import time
+import weakref
 
 import numpy as np
 import torch
@@ -26,6 +29,103 @@ from . import objectives, ops
 CAPS_PER_IMG = 5   # hard-coded upstream, evaluation.py:173,208
 
 
+# ----------------------------------------------------------------------------------------- host hand-off
+class _PinnedPool:
+    """Page-locked host buffers for the matrices ``cal_sims`` hands back, recycled when the array (and every view of
+    it) has been garbage-collected.  Bounded: beyond ``ITR_B200_PINNED_POOL_MB`` (default 4096) the caller gets
+    pageable memory, as with the reference."""
+
+    def __init__(self):
+        self.free, self.lock, self.bytes = [], threading.Lock(), 0
+        self.cap = int(os.environ.get("ITR_B200_PINNED_POOL_MB", "4096")) << 20
+
+    def take(self, nbytes):
+        """A pinned uint8 tensor of at least nbytes, or None when the pool is exhausted / pinning fails."""
+        with self.lock:
+            fits = [t for t in self.free if nbytes <= t.numel() <= max(2 * nbytes, 1 << 20)]
+            if fits:
+                t = min(fits, key=lambda x: x.numel())
+                self.free.remove(t)
+                return t
+            if self.bytes + nbytes > self.cap:
+                drop = sorted(self.free, key=lambda x: -x.numel())
+                while drop and self.bytes + nbytes > self.cap:
+                    t = drop.pop(0)
+                    self.free.remove(t)
+                    self.bytes -= t.numel()
+                if self.bytes + nbytes > self.cap:
+                    return None
+            self.bytes += nbytes
+        try:
+            return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:
+            with self.lock:
+                self.bytes -= nbytes
+            return None
+
+    def give_back(self, t):
+        with self.lock:
+            self.free.append(t)
+
+
+_POOL = _PinnedPool()
+
+
+def _release_pinned(t):
+    _POOL.give_back(t)
+
+
+class _SimsEntry:
+    __slots__ = ("ref", "dev", "ranks")
+
+    def __init__(self, ref, dev):
+        self.ref, self.dev, self.ranks = ref, dev, None
+
+
+_SIMS = {}      # id(host array cal_sims returned) -> _SimsEntry (device matrix it was copied from)
+
+
+def _remember(arr, dev_matrix):
+    key = id(arr)
+    _SIMS[key] = _SimsEntry(weakref.ref(arr, lambda _r, k=key: _SIMS.pop(k, None)), dev_matrix)
+
+
+def _device_twin(sims):
+    """The cache entry of the device matrix behind a host array ``cal_sims`` returned, or None.  The host array is
+    handed out read-only; if somebody made it writeable again its contents may have changed, so the twin is dropped."""
+    if not isinstance(sims, np.ndarray):
+        return None
+    e = _SIMS.get(id(sims))
+    if e is None or e.ref() is not sims:
+        return None
+    if sims.flags.writeable:
+        _SIMS.pop(id(sims), None)
+        return None
+    return e
+
+
+def _to_host_f64(d):
+    """CUDA f32 (n_img, n_cap) -> host float64 ndarray: converted on the device, one DMA into a recycled pinned
+    buffer (pageable when the pool is exhausted).  The result is marked read-only (see _device_twin)."""
+    n = d.numel()
+    if n == 0:
+        return np.zeros(tuple(d.shape), dtype=np.float64)
+    d64 = d.double()
+    buf = _POOL.take(n * 8)
+    if buf is None:
+        out = d64.cpu().numpy()
+    else:
+        host = buf[: n * 8].view(torch.float64).view(d.shape)
+        host.copy_(d64, non_blocking=True)
+        torch.cuda.current_stream(d.device).synchronize()
+        root = buf.numpy()
+        weakref.finalize(root, _release_pinned, buf)
+        out = root[: n * 8].view(np.float64).reshape(tuple(d.shape))
+        del root
+    out.setflags(write=False)
+    return out
+
+
 def _device():
     if not torch.cuda.is_available():
         raise RuntimeError("itr_b200 needs a CUDA device; there is no CPU fallback")
@@ -33,11 +133,16 @@ def _device():
 
 
 def _to_device(x, dev):
-    """host numpy / tensor -> CUDA f32 tensor (pinned tensors copy asynchronously)."""
+    """host numpy / tensor -> CUDA f32 tensor.  Pinned memory copies asynchronously in one DMA; large PAGEABLE arrays
+    (the reference de-duplicates the images with a list comprehension, evaluation.py:289, so what reaches cal_sims
+    is a fresh pageable copy) go through ops.upload_pageable: chunks staged into two pinned buffers by a
+    multi-threaded host copy that overlaps the DMA of the previous chunk."""
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(np.ascontiguousarray(x))
     if x.dtype != torch.float32:
         x = x.float()
+    if not x.is_cuda and not x.is_pinned() and x.numel() * 4 >= ops.STAGED_UPLOAD_MIN_BYTES:
+        return ops.upload_pageable(x.contiguous(), dev)
     return x.to(dev, non_blocking=True)
 
 
@@ -76,33 +181,34 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
     fused = cal_fun in (objectives.cosine_sim, objectives.xattn_score_t2i, objectives.xattn_score_i2t)
     with torch.no_grad():
         if fused:
-            norm_ = config.get("raw_feature_norm")
-            sharded = (image_group is not None and cal_fun is objectives.xattn_score_t2i
-                       and objectives._precision(config) == "bf16" and norm_ in ("clipped_l2norm", "l2norm")
-                       and getattr(img_embs, "ndim", 0) == 3 and tuple(img_embs.shape[1:]) == (36, 1024)
-                       and ln is not None and int(np.max(ln)) <= 128)
-            if sharded:
+            norm = config.get("raw_feature_norm")
+            # the fused tcgen05 t2i kernel: decided from rank-invariant inputs (config, image shape) ...
+            tc_t2i = (cal_fun is objectives.xattn_score_t2i and objectives._precision(config) == "bf16"
+                      and norm in ("clipped_l2norm", "l2norm") and ln is not None
+                      and getattr(img_embs, "ndim", 0) == 3 and tuple(img_embs.shape[1:]) == (36, 1024)
+                      and getattr(cap_embs, "ndim", 0) == 3 and cap_embs.shape[2] == 1024)
+            # ... and from the caption lengths, which are rank-LOCAL when the captions are sharded: the sharded path
+            # runs collectives (image all-gather), so every rank must take the same branch -- agree on one flag first
+            # (an empty local block is fine: nothing to score, but the rank still joins the all-gather).
+            lens_ok = tc_t2i and (ln.size == 0 or (int(np.min(ln)) >= 1 and int(np.max(ln)) <= ops.TC_MAX_WORDS))
+            if tc_t2i and image_group is not None:
+                lens_ok = ops.all_ranks_agree(lens_ok, image_group, dev)
+            if tc_t2i and lens_ok:
                 caps = cap_embs if isinstance(cap_embs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cap_embs))
                 if caps.dtype != torch.float32:
                     caps = caps.float()
                 if not caps.is_cuda and not caps.is_pinned():
-                    caps = caps.to(dev)
-                pi = ops.prepare_images_sharded(img_embs, image_group, dev)
-                return _scan_t2i_from(pi, caps, ln, norm_, config, dev)
+                    caps = _to_device(caps, dev)          # pageable host memory: staged copy of the padded array
+                if image_group is not None:
+                    pi = ops.prepare_images_sharded(img_embs, image_group, dev)
+                else:
+                    pi = ops.prepare_images(_to_device(img_embs, dev))
+                if n_cap == 0:
+                    return torch.empty(n_img, 0, device=dev, dtype=torch.float32)
+                return _scan_t2i_from(pi, caps, ln, norm, config, dev)
             img = _to_device(img_embs, dev)
             if cal_fun is objectives.cosine_sim:
                 return ops.cosine_scores(img, _to_device(cap_embs, dev))
-            norm, agg = config["raw_feature_norm"], config["agg_func"]
-            if (cal_fun is objectives.xattn_score_t2i and objectives._precision(config) == "bf16"
-                    and img.dim() == 3 and img.size(1) == 36 and img.size(2) == 1024 and norm in ("clipped_l2norm", "l2norm")
-                    and int(np.max(ln)) <= 128):
-                caps = cap_embs if isinstance(cap_embs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cap_embs))
-                if caps.dtype != torch.float32:
-                    caps = caps.float()
-                if not caps.is_cuda and not caps.is_pinned():
-                    caps = caps.to(dev)          # pageable host memory: one plain copy
-                pi = ops.prepare_images(img)
-                return _scan_t2i_from(pi, caps, ln, norm, config, dev)
             return cal_fun(img, _to_device(cap_embs, dev), ln, config)
         # anything else (learned similarity heads, CAMERA): the reference's blocked loop, with sliced lengths
         out = torch.empty(n_img, n_cap, device=dev, dtype=torch.float32)
@@ -174,10 +280,18 @@ def encode_data(model, data_loader, islength=False):
 
 
 def cal_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False):
-    """evaluation.py:124-153: host numpy in, host float64 (n_img, n_cap) out."""
+    """evaluation.py:124-153: host numpy in, host float64 (n_img, n_cap) out.
+
+    The returned array is a genuine float64 ndarray (filled by one DMA from the device, read-only) and the device
+    matrix it came from is remembered behind it: ``cal_recall`` / ``i2t`` / ``t2i`` called with that same array
+    (evaluation.py:290-291, utils.py:158-167) rank from the device copy, both directions in one pass, instead of
+    uploading the matrix again.  Anything derived from it (a copy, an average of two matrices) is ranked from the
+    host values as before."""
     t0 = time.time()
     d = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths)
-    out = d.cpu().numpy().astype(np.float64)
+    out = _to_host_f64(d)
+    if out.size:
+        _remember(out, d)
     print("Calculate similarity matrix elapses: {:.3f}s".format(time.time() - t0))
     return out
 
@@ -205,6 +319,11 @@ def device_ranks(sims_dev, caps_per_img=CAPS_PER_IMG):
 
 
 def _rank_host(sims):
+    twin = _device_twin(sims)
+    if twin is not None:
+        if twin.ranks is None:
+            twin.ranks = [x.cpu().numpy().astype(np.float64) for x in device_ranks(twin.dev)]
+        return [r.copy() for r in twin.ranks]
     dev = _device()
     if isinstance(sims, torch.Tensor):
         s = sims.to(dev)

@@ -34,6 +34,48 @@ def lengths_to_numpy(cap_lens, n_cap):
     return ln
 
 
+STAGED_UPLOAD_MIN_BYTES = 32 << 20
+_STAGING = {}
+
+
+def upload_pageable(x, dev, chunk_bytes=32 << 20):
+    """Pageable host f32 tensor -> CUDA tensor at close to the PCIe rate: the array is cut into chunks, each chunk is
+    copied into one of two pinned staging buffers (torch's CPU copy is multi-threaded) and DMA'd from there, so the
+    host copy of chunk k+1 overlaps the DMA of chunk k.  A plain ``.to(device)`` of pageable memory is staged by the
+    driver single-threaded at a fraction of that."""
+    dev = torch.device(dev)
+    out = torch.empty(x.shape, dtype=x.dtype, device=dev)
+    flat_src, flat_dst = x.reshape(-1), out.reshape(-1)
+    n = flat_src.numel()
+    per = max(1, chunk_bytes // x.element_size())
+    key = (x.dtype, per)
+    if key not in _STAGING:
+        _STAGING[key] = ([torch.empty(per, dtype=x.dtype, pin_memory=True) for _ in range(2)], [None, None])
+    bufs, events = _STAGING[key]
+    stream = torch.cuda.current_stream(dev)
+    for k, lo in enumerate(range(0, n, per)):
+        hi = min(lo + per, n)
+        b = k & 1
+        if events[b] is not None:
+            events[b].synchronize()                     # the DMA that last read this staging buffer is done
+        bufs[b][: hi - lo].copy_(flat_src[lo:hi])
+        flat_dst[lo:hi].copy_(bufs[b][: hi - lo], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        events[b] = ev
+    return out
+
+
+def _trim_to_longest(captions, ln):
+    """captions (n_cap, lmax, d) -> (captions[:, :max(ln)] contiguous, max(ln)): the float32 kernels size their
+    shared-memory tiles by the width they are given (<= 96 words), so hand them the true longest caption."""
+    lmax = captions.size(1)
+    longest = int(ln.max()) if len(ln) else lmax
+    if 1 <= longest < lmax:
+        return captions[:, :longest].contiguous(), longest
+    return captions, lmax
+
+
 # ------------------------------------------------------------------------------ VSE++
 def cosine_scores(im, s):
     im, s = _cuda_f32(im, "im"), _cuda_f32(s, "s")
@@ -128,6 +170,7 @@ def scan_scores_f32(images, captions, cap_lens, cross_attn, raw_feature_norm, ag
     out = torch.empty(n_img, n_cap, device=images.device, dtype=torch.float32)
     if out.numel() == 0:
         return out
+    captions, lmax = _trim_to_longest(captions, ln)
     lens_dev = torch.from_numpy(ln).to(images.device)
     L = capi.lib()
     with torch.cuda.device(images.device):
@@ -163,9 +206,14 @@ def scan_backward_f32(images, captions, cap_lens, d_scores, cross_attn, raw_feat
     cross = capi.T2I if cross_attn == "t2i" else capi.I2T
     dev = images.device
     d_images = torch.empty_like(images)
-    d_captions = torch.zeros_like(captions)
+    d_captions_full = torch.zeros_like(captions)
     if n_img == 0 or n_cap == 0:
-        return d_images.zero_(), d_captions
+        return d_images.zero_(), d_captions_full
+    captions, lmax_used = _trim_to_longest(captions, ln)
+    # the kernels see the batch's true longest caption (<= 96 words), whatever the padded width; the gradient of the
+    # columns beyond it is zero
+    d_captions = d_captions_full if lmax_used == lmax else torch.zeros_like(captions)
+    lmax = lmax_used
     l64 = ln.astype(np.int64)
     n_words, sum_sq = int(l64.sum()), int((l64 * l64).sum())
     lens_dev = torch.from_numpy(ln).to(dev)
@@ -189,7 +237,9 @@ def scan_backward_f32(images, captions, cap_lens, d_scores, cross_attn, raw_feat
                                           ptr(lens_dev), i1 - i0, n_reg, n_cap, lmax, d, n_words, sum_sq, cross, norm, agg,
                                           float(lambda_softmax), float(lambda_lse), ptr(ds), ds.stride(0),
                                           ptr(d_images[i0:i1]), ptr(d_captions), ptr(ws), ws_bytes, stream_ptr()))
-    return d_images, d_captions
+    if d_captions is not d_captions_full:
+        d_captions_full[:, :lmax].copy_(d_captions)
+    return d_images, d_captions_full
 
 
 # ------------------------------------------------------------------------------ SCAN t2i, tensor cores
@@ -210,6 +260,7 @@ class PreparedCaptions:
     sum_len: int
 
 
+TC_MAX_WORDS = 128           # longest caption the fused tcgen05 t2i kernel scores (one 128-row word tile)
 GENERIC_MAX_WORDS = 100      # longest caption whose phase-2 tile fits in shared memory (2*144*(n+1) + (n+1)^2 floats)
 
 
@@ -222,6 +273,24 @@ def tc_shapes(images, captions):
 def tc_supported(images, captions, raw_feature_norm, cap_lens=None):
     """Shapes / modes the FUSED tcgen05 t2i kernel is built for."""
     return tc_shapes(images, captions) and raw_feature_norm in ("clipped_l2norm", "l2norm")
+
+
+_PLAN_CACHE = {}       # (device, digest of the lengths) -> (row_meta on the device, n_tiles); a validation set is re-planned every epoch otherwise
+
+
+def plan_words_device(lengths: np.ndarray, device):
+    """plan_words + the upload of the row metadata, memoised on the lengths array (LRU of 16 plans per process)."""
+    import hashlib
+    lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+    key = (str(device), len(lengths), hashlib.blake2b(lengths.tobytes(), digest_size=16).digest())
+    hit = _PLAN_CACHE.pop(key, None)
+    if hit is None:
+        meta_host, n_tiles = plan_words(lengths)
+        hit = (torch.from_numpy(meta_host).to(device), n_tiles)
+    _PLAN_CACHE[key] = hit                      # most recently used last
+    while len(_PLAN_CACHE) > 16:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    return hit
 
 
 def plan_words(lengths: np.ndarray):
@@ -257,7 +326,10 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
-        return prepare_images(t.to(device if device is not None else "cuda", non_blocking=True))
+        d_ = torch.device(device if device is not None else "cuda")
+        if not t.is_cuda and not t.is_pinned() and t.dtype == torch.float32 and t.numel() * 4 >= STAGED_UPLOAD_MIN_BYTES:
+            return prepare_images(upload_pageable(t.contiguous(), d_))
+        return prepare_images(t.to(d_, non_blocking=True))
     rank = dist.get_rank(group)
     n_img = len(images)
     per = (n_img + world - 1) // world
@@ -266,7 +338,12 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
     sl = images[lo:hi]
     if not isinstance(sl, torch.Tensor):
         sl = torch.from_numpy(np.ascontiguousarray(sl))
-    sl = sl.to(dev, non_blocking=True)
+    if sl.dtype != torch.float32:
+        sl = sl.float()
+    if not sl.is_cuda and not sl.is_pinned() and sl.numel() * 4 >= STAGED_UPLOAD_MIN_BYTES:
+        sl = upload_pageable(sl.contiguous(), dev)
+    else:
+        sl = sl.to(dev, non_blocking=True)
     img_all = torch.empty(world * per, capi.REGIONS, capi.EMBED, device=dev, dtype=torch.bfloat16)
     gram_all = torch.empty(world * per, capi.GRAM_BYTES, device=dev, dtype=torch.uint8)
     img_loc = img_all[rank * per:(rank + 1) * per]          # all_gather_into_tensor may gather in place
@@ -278,9 +355,20 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
     if hi - lo < per:
         img_loc[hi - lo:].zero_()
         gram_loc[hi - lo:].zero_()
-    dist.all_gather_into_tensor(img_all, img_loc.clone(), group=group)
-    dist.all_gather_into_tensor(gram_all, gram_loc.clone(), group=group)
+    dist.all_gather_into_tensor(img_all, img_loc, group=group)       # in place: each rank's slice is already where it belongs
+    dist.all_gather_into_tensor(gram_all, gram_loc, group=group)
     return PreparedImages(img_all[:n_img], gram_all[:n_img], n_img)
+
+
+def all_ranks_agree(flag: bool, group, device) -> bool:
+    """True iff `flag` is true on every rank of `group` (one all-reduce(MIN) of an int; no-op without a process group)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(flag)
+    backend = dist.get_backend(group)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device if backend == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
 
 
 def prepare_captions(captions, cap_lens, device=None) -> PreparedCaptions:
@@ -299,8 +387,7 @@ def prepare_captions(captions, cap_lens, device=None) -> PreparedCaptions:
     ln = lengths_to_numpy(cap_lens, n_cap)
     if n_cap and ln.max() > lmax:
         raise ValueError("caption length {} exceeds the padded width {}".format(int(ln.max()), lmax))
-    meta_host, n_tiles = plan_words(ln)
-    meta = torch.from_numpy(meta_host).to(device, non_blocking=False)
+    meta, n_tiles = plan_words_device(ln, device)
     rows = n_tiles * capi.TILE_WORDS
     words = torch.empty(rows, capi.EMBED, device=device, dtype=torch.bfloat16)
     wnorm = torch.empty(rows, device=device, dtype=torch.float32)
@@ -403,6 +490,9 @@ def scan_scores_tc_generic(images, captions, cap_lens, cross_attn, raw_feature_n
     if pi is None:
         pi = prepare_images(images)
     ln = lengths_to_numpy(cap_lens, len(cap_lens))
+    if len(ln) and (ln.min() < 1 or ln.max() > GENERIC_MAX_WORDS):
+        raise ValueError("the two-phase tensor-core path scores captions of 1..{} words, got {}..{}; use the float32 mode "
+                         "(itr_b200_precision='fp32')".format(GENERIC_MAX_WORDS, int(ln.min()), int(ln.max())))
     if pc is None:
         pc = prepare_captions(captions, ln)
     dev = pi.images_bf16.device

@@ -6,11 +6,11 @@ of ``caps_per_img`` (an image's ground-truth captions stay together), every rank
 images.  Ranking needs one small exchange:
 
   t2i  fully local -- a rank owns whole columns, so the rank and top-1 of its captions are exact;
-       the per-caption vectors are merged with one all-reduce (each rank contributes its slice).
+       the per-caption vectors are concatenated.
   i2t  the threshold of image i is its best ground-truth score, which lives on exactly one rank:
        all-reduce(MAX) of a (n_img,) float vector; then every rank counts the local captions that
-       beat it and the counts are all-reduced (SUM); the global top-1 is an all-reduce(MAX) of a
-       packed (score, caption) key.
+       beat it; counts are summed and the packed (score, caption) arg-max keys maxed.
+  Everything after the threshold all-reduce travels in ONE all-gather of a packed int64 vector per rank.
 
 All payloads are KBs, so the exchange is latency-bound; counts are integers, so the result is
 bit-identical for every world size.  ``torch.distributed`` (NCCL over NVLink on the box, gloo in
@@ -53,8 +53,14 @@ class CudaStats:
         return cnt_row, cnt_col, best_row ^ _SIGN, ops.unpack_best_index(best_col)
 
 
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
 def _all_reduce(t, op, group):
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if _world(group) > 1:
         dist.all_reduce(t, op=op, group=group)
     return t
 
@@ -63,28 +69,44 @@ def sharded_ranks(block, start, n_cap_total, group=None, caps_per_img=5, stats=C
     """block: this rank's (n_img, n_local) scores, first column = global caption ``start``.
     Returns (i2t_ranks, i2t_top1, t2i_ranks, t2i_top1) as int64 tensors, identical on every rank.
 
-    best_row keys handed over by ``stats.count`` are signed-comparable int64 (unsigned key ^ 2^63)
-    whose low 32 bits hold ~(global caption index)."""
+    Two collectives: all-reduce(MAX) of the i2t thresholds, then ONE all-gather of every rank's packed int64
+    statistics [i2t counts | i2t arg-max keys | t2i ranks of its captions | t2i top-1 of its captions]; the merge
+    (sum of counts, max of keys, concatenation of the caption slices) is local.  best_row keys handed over by
+    ``stats.count`` are signed-comparable int64 (unsigned key ^ 2^63) whose low 32 bits hold ~(global caption index)."""
     n_img, n_local = block.shape
     dev = block.device
+    world = _world(group)
     if n_local > 0:
         thr_row, thr_col = stats.thresholds(block, start, caps_per_img)
     else:
         thr_row = torch.full((n_img,), float("-inf"), device=dev)
         thr_col = torch.empty(0, device=dev)
     thr_row = _all_reduce(thr_row.contiguous(), dist.ReduceOp.MAX, group)
-    merged = torch.zeros(n_img + 2 * n_cap_total, dtype=torch.int64, device=dev)
-    best = torch.full((n_img,), _SIGN, dtype=torch.int64, device=dev)
+    bounds = shard_bounds(n_cap_total, world, caps_per_img) if world > 1 else [(start, start + n_local)]
+    width = max(hi - lo for lo, hi in bounds)
+    mine = torch.zeros(2 * n_img + 2 * width, dtype=torch.int64, device=dev)
+    mine[n_img: 2 * n_img] = _SIGN
     if n_local > 0:
         cnt_row, cnt_col, best_row, best_col_idx = stats.count(block, thr_row, thr_col, start)
-        merged[:n_img] = cnt_row
-        merged[n_img + start: n_img + start + n_local] = cnt_col
-        merged[n_img + n_cap_total + start: n_img + n_cap_total + start + n_local] = best_col_idx
-        best = best_row.contiguous()
-    merged = _all_reduce(merged, dist.ReduceOp.SUM, group)
-    best = _all_reduce(best, dist.ReduceOp.MAX, group)
+        mine[:n_img] = cnt_row
+        mine[n_img: 2 * n_img] = best_row
+        mine[2 * n_img: 2 * n_img + n_local] = cnt_col
+        mine[2 * n_img + width: 2 * n_img + width + n_local] = best_col_idx
+    if world > 1:
+        if bounds[dist.get_rank(group)] != (start, start + n_local):
+            raise ValueError("sharded_ranks: this rank's block ({}, {}) is not shard_bounds()[rank] = {}".format(
+                start, start + n_local, bounds[dist.get_rank(group)]))
+        every = torch.empty(world * mine.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        every = every.view(world, -1)
+    else:
+        every = mine.view(1, -1)
+    i2t_ranks = every[:, :n_img].sum(dim=0)
+    best = every[:, n_img: 2 * n_img].max(dim=0).values
     i2t_top1 = (~best) & 0xFFFFFFFF
-    return merged[:n_img], i2t_top1, merged[n_img: n_img + n_cap_total], merged[n_img + n_cap_total:]
+    t2i_ranks = torch.cat([every[r, 2 * n_img: 2 * n_img + (hi - lo)] for r, (lo, hi) in enumerate(bounds)])
+    t2i_top1 = torch.cat([every[r, 2 * n_img + width: 2 * n_img + width + (hi - lo)] for r, (lo, hi) in enumerate(bounds)])
+    return i2t_ranks, i2t_top1, t2i_ranks, t2i_top1
 
 
 def sharded_scan_eval(images, captions_local, lengths_local, start, n_cap_total, config, group=None,

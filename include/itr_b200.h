@@ -175,6 +175,9 @@ int itr_scan_t2i_profile(const uint16_t* images_bf16, const void* gram_pack, int
 /* Tuning: cycles until `n_issuers` warps have each pushed `iters` tcgen05.mma (M=128, K=16, kind::f16) through the
  * tensor pipe of one CTA, on `n_ctas` CTAs; see csrc/scan_t2i_tc.cu.  cycles[n_ctas]. */
 int itr_tc_mma_microbench(int n_cols, int n_acc, int iters, int a_tmem, int kadv, int n_issuers, int n_ctas, int64_t* cycles, void* stream);
+/* Tuning: the same for the CTA-pair form (tcgen05.mma.cta_group::2, M=256 across the two SMs of a cluster of 2; each CTA
+ * supplies N/2 rows of B), on `n_pairs` clusters; see csrc/tc_microbench2.cu.  cycles[n_pairs]. */
+int itr_tc_mma2_microbench(int n_cols, int n_acc, int iters, int a_tmem, int n_issuers, int n_pairs, int64_t* cycles, void* stream);
 
 /* ---- hinge loss: ContrastiveLoss.forward / TripletLoss.forward, Objectives.py:93-115, 492-517
  * loss (1 float, device) = sum of both directions; dscores (n x n, may be NULL) = dloss/dscores. */

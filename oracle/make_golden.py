@@ -14,7 +14,9 @@ reference's own functions on them:
   evaluation.i2t / t2i                            (itr/metricmodule/evaluation.py:156-222)
   torch autograd through xattn_score_* (+ TripletLoss)   -> scan_grad.npz, the pin of the training backward
 
-    python oracle/make_golden.py --only scan_grad        regenerates that file alone
+  Objectives.func_attention / cosine_similarity / pdist / pdist_cos   -> helpers.npz
+
+    python oracle/make_golden.py --only scan_grad        regenerates that file alone (also: aux_sims, helpers)
 """
 from __future__ import annotations
 
@@ -157,6 +159,42 @@ def aux_sims_case(O, name="aux_sims", seed=106):
     print(name, len(out), "arrays")
 
 
+def helpers_case(O, name="helpers", seed=107):
+    """The small exported helpers, from the reference's own code: func_attention (Objectives.py:421-476) for every
+    raw_feature_norm in both roles, cosine_similarity (:10-15), SAEM's pdist / pdist_cos (:296-323)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    b, n_q, n_ctx, d = 3, 7, 36, 64
+    query = torch.randn(b, n_q, d, generator=g)
+    context = torch.nn.functional.normalize(torch.randn(b, n_ctx, d, generator=g), dim=-1)
+    q_bits, c_bits = bf16_bits(query), bf16_bits(context)
+    query, context = from_bits(q_bits).double(), from_bits(c_bits).double()
+    out.update({"fa|query_bits": q_bits, "fa|context_bits": c_bits})
+    for norm in NORMS:
+        for smooth in (9.0, 4.0):
+            with torch.no_grad():
+                w, a = O.func_attention(query, context, dict(raw_feature_norm=norm), smooth=smooth)
+            out["fa|{}|{}|weighted".format(norm, smooth)] = w.numpy()
+            out["fa|{}|{}|attn".format(norm, smooth)] = a.numpy()
+    x1 = torch.randn(5, 9, d, generator=g)
+    x2 = torch.randn(5, 9, d, generator=g)
+    x2[2, 4] = 0.0                                               # a zero row: the clamp(min=eps) branch
+    x1_bits, x2_bits = bf16_bits(x1), bf16_bits(x2)
+    x1, x2 = from_bits(x1_bits).double(), from_bits(x2_bits).double()
+    out.update({"cs|x1_bits": x1_bits, "cs|x2_bits": x2_bits,
+                "cs|dim2": O.cosine_similarity(x1, x2, dim=2).numpy(),
+                "cs|dim1": O.cosine_similarity(x1, x2, dim=1).numpy()})
+    a = torch.randn(17, 96, generator=g)
+    bb = torch.randn(23, 96, generator=g)
+    bb[5] = 0.0                                                  # pdist_cos zeroes the NaNs of 0/0
+    a_bits, b_bits = bf16_bits(a), bf16_bits(bb)
+    a, bb = from_bits(a_bits).double(), from_bits(b_bits).double()
+    out.update({"pd|x1_bits": a_bits, "pd|x2_bits": b_bits, "pd|pdist": O.pdist(a, bb).numpy(),
+                "pd|pdist_cos": O.pdist_cos(a, bb).numpy()})
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, len(out), "arrays")
+
+
 def main():
     O, E = ref_loader.load()
     torch.set_num_threads(8)
@@ -168,14 +206,17 @@ def main():
             scan_grad_case(O)
         elif only == "aux_sims":
             aux_sims_case(O)
+        elif only == "helpers":
+            helpers_case(O)
         else:
-            raise SystemExit("--only supports: scan_grad, aux_sims")
+            raise SystemExit("--only supports: scan_grad, aux_sims, helpers")
         return
 
     scan_case(O, "scan_small", n_img=8, lens=[16, 3, 12, 9, 5, 14, 7, 11, 16, 4, 13, 8], seed=101)
     scan_case(O, "scan_long", n_img=5, lens=[72, 40, 33], seed=102)
     scan_grad_case(O)
     aux_sims_case(O)
+    helpers_case(O)
 
     # cosine + hinge
     g = torch.Generator().manual_seed(103)

@@ -15,6 +15,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device and the built library; on a box without them they are skipped (the CPU suite
+    is selected with -m "not gpu"; a plain `pytest tests` must not fail there)."""
+    try:
+        import torch
+        have = torch.cuda.is_available() and os.path.exists(os.path.join(ROOT, "image-text-retrieval_b200", "libitr_b200.so"))
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device and libitr_b200.so")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -82,10 +82,95 @@ def test_config5_coco5k_shape_full():
     f32 = ops.scan_scores_f32(img[:256], cap[cols], lens[cols.cpu().numpy()], "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
     rel = ((a[:256][:, cols] - f32).abs() / f32.abs().clamp_min(1e-6)).max().item()
     assert rel < 1.5e-3, rel          # inputs here are NOT pre-rounded: bf16 input quantisation included
+    # the oracle (float64, the reference's algorithm) on a column block: first 32 images x captions incl. two planted
+    # long ones (72 and 59 words), fed the bf16-rounded values the kernel consumes
+    ocols = np.array([0, 997, 12345, 24999])
+    rnd = lambda t: t.to(torch.bfloat16).float().cpu().numpy()
+    want = so.scan_scores(rnd(img[:32]), rnd(cap[torch.from_numpy(ocols).cuda()]), lens[ocols], "t2i", "clipped_l2norm",
+                          "LogSumExp", 9.0, 6.0)
+    np.testing.assert_allclose(a[:32][:, torch.from_numpy(ocols).cuda()].cpu().numpy(), want, rtol=1e-3, atol=1e-6)
+    assert lens[0] == 72 and lens[997] == 71
     i2t, _, t2i, _ = ev.device_ranks(a)
     vi, vt = virtual_shard_ranks(a, 8)
     assert torch.equal(vi, i2t) and torch.equal(vt, t2i)
     assert (t2i < 1).float().mean().item() > 0.9 and (i2t < 10).float().mean().item() > 0.9
+
+
+def _ranks_match_up_to_ties(got, want_ranks, scores64, thr, axis, tol):
+    """ranks equal except where another reference score sits within `tol` of the ground-truth score (north_star)."""
+    got = np.asarray(got, dtype=np.int64)
+    want_ranks = np.asarray(want_ranks, dtype=np.int64)
+    bad = np.nonzero(got != want_ranks)[0]
+    for q in bad:
+        line = scores64[q] if axis == 1 else scores64[:, q]
+        near = int(np.count_nonzero(np.abs(line - thr[q]) <= tol)) - 1
+        assert abs(int(got[q]) - int(want_ranks[q])) <= near, (q, got[q], want_ranks[q], near)
+    return len(bad)
+
+
+def test_config1_vse_cosine_recall_full():
+    """BASELINE config 1 at its stated size: VSE++ cosine scores + i2t/t2i Recall@K, 1000 x 5000 x 1024."""
+    im, s = itr_b200.synth.vse_inputs(1000, 5000, 1, device="cuda")
+    scores = ops.cosine_scores(im, s)
+    want = so.cosine_scores(im.cpu().numpy(), s.cpu().numpy())                 # float64
+    np.testing.assert_allclose(scores.cpu().numpy(), want, rtol=1e-5, atol=2e-6)
+    # the rank kernels are exact on the matrix they are given ...
+    i2t, top_i, t2i, top_c = [x.cpu().numpy() for x in ev.device_ranks(scores)]
+    s32 = scores.double().cpu().numpy()
+    ri, rt, tied_i, tied_c = so.strict_ranks(s32)
+    np.testing.assert_array_equal(i2t, ri)
+    np.testing.assert_array_equal(t2i, rt)
+    np.testing.assert_array_equal(top_i[~tied_i], s32.argmax(axis=1)[~tied_i])
+    np.testing.assert_array_equal(top_c[~tied_c], s32.argmax(axis=0)[~tied_c])
+    # ... and agree with the reference's argsort ranking of the float64 matrix except at within-tolerance ties
+    rd = so.recall_dict(want)
+    gt = 5 * np.arange(1000)[:, None] + np.arange(5)[None, :]
+    thr_i = np.take_along_axis(want, gt, axis=1).max(axis=1)
+    thr_c = want[np.arange(5000) // 5, np.arange(5000)]
+    n_bad = _ranks_match_up_to_ties(i2t, rd["i2t_ranks"], want, thr_i, 1, 4e-6)
+    n_bad += _ranks_match_up_to_ties(t2i, rd["t2i_ranks"], want, thr_c, 0, 4e-6)
+    assert n_bad <= 30, n_bad
+    # through the drop-in entry points: host numpy in, the reference's dict out
+    m = type("M", (), {"sim_enc": None})()
+    m.config = cfg(name="VSE++")
+    m.criterion = ob.ContrastiveLoss(m.config, margin=0.2, measure="cosine", max_violation=True)
+    res = ev.cal_sims_and_recall(m, im.cpu().numpy(), s.cpu().numpy())
+    np.testing.assert_array_equal(res["i2t_ranks"], i2t)
+    np.testing.assert_array_equal(res["t2i_ranks"], t2i)
+    assert abs(res["rsum"] - rd["rsum"]) <= 0.3
+
+
+def test_config4_coco_5fold_i2t_mean_full():
+    """BASELINE config 4 at its stated size: SCAN i2t Mean (lambda_softmax 4), 5 folds of 1000 images x 5000 captions
+    with the COCO-shaped lengths, tensor-core mode against the float64 oracle on a block per fold (incl. the fold's
+    longest caption) and against the float32 mode on every rank."""
+    lens_all = itr_b200.synth.caption_lengths(25000, 10.5, 14)
+    c4 = cfg(cross_attn="i2t", agg_func="Mean", lambda_softmax=4.0)
+    rnd = lambda t: t.to(torch.bfloat16).float()
+    for fold in range(5):
+        lengths = lens_all[fold * 5000:(fold + 1) * 5000]
+        img, cap, ln = itr_b200.synth.scan_inputs(1000, 5000, 10.5, 14 + fold, device="cuda", lengths=lengths, round_to="bf16")
+        a = ob.xattn_score_i2t(img, cap, ln, c4)
+        assert a.shape == (1000, 5000) and torch.isfinite(a).all()
+        assert torch.equal(a, ob.xattn_score_i2t(img, cap, ln, c4))               # deterministic
+        longest = int(np.argmax(ln))
+        ocols = np.unique(np.concatenate([np.arange(15), [longest, 4999]]))
+        assert ln[longest] >= 44
+        oc = torch.from_numpy(ocols).cuda()
+        want = so.scan_scores(img[:32].cpu().numpy(), cap[oc].cpu().numpy(), ln[ocols], "i2t", "clipped_l2norm", "Mean", 4.0, 6.0)
+        np.testing.assert_allclose(a[:32][:, oc].cpu().numpy(), want, rtol=1e-3, atol=1e-6)
+        if fold in (0, 3):
+            # float32 CUDA-core mode on the whole fold: scores within the bf16 contract, recall identical up to near-ties
+            f32 = ob.xattn_score_i2t(img, cap, ln, dict(c4, itr_b200_precision="fp32"))
+            rel = ((a - f32).abs() / f32.abs().clamp_min(1e-6)).max().item()
+            assert rel < 1e-3, rel
+            ra, rb = ev.device_ranks(a), ev.device_ranks(f32)
+            rsum = lambda r: sum(100.0 * (r[0] < k).float().mean().item() + 100.0 * (r[2] < k).float().mean().item() for k in (1, 5, 10))
+            assert abs(rsum(ra) - rsum(rb)) <= 0.2, (rsum(ra), rsum(rb))
+            assert (ra[0] != rb[0]).float().mean().item() < 0.01 and (ra[2] != rb[2]).float().mean().item() < 0.01
+        i2t, _, t2i, _ = ev.device_ranks(a)
+        assert int(i2t.max()) < 5000 and int(t2i.max()) < 1000
+        assert (t2i < 10).float().mean().item() > 0.9
 
 
 def test_config2_hinge_batch128_timing_sanity():
