@@ -42,17 +42,13 @@ class _PinnedPool:
     def take(self, nbytes):
         """A pinned uint8 tensor of at least nbytes, or None when the pool is exhausted / pinning fails."""
         with self.lock:
-            fits = [t for t in self.free if nbytes <= t.numel() <= max(2 * nbytes, 1 << 20)]
+            fits = [i for i, t in enumerate(self.free) if nbytes <= t.numel() <= max(2 * nbytes, 1 << 20)]
             if fits:
-                t = min(fits, key=lambda x: x.numel())
-                self.free.remove(t)
-                return t
+                return self.free.pop(min(fits, key=lambda i: self.free[i].numel()))      # by index: `in` / remove() compare tensors elementwise
             if self.bytes + nbytes > self.cap:
-                drop = sorted(self.free, key=lambda x: -x.numel())
-                while drop and self.bytes + nbytes > self.cap:
-                    t = drop.pop(0)
-                    self.free.remove(t)
-                    self.bytes -= t.numel()
+                while self.free and self.bytes + nbytes > self.cap:
+                    i = max(range(len(self.free)), key=lambda j: self.free[j].numel())
+                    self.bytes -= self.free.pop(i).numel()
                 if self.bytes + nbytes > self.cap:
                     return None
             self.bytes += nbytes

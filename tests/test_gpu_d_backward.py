@@ -137,9 +137,20 @@ def test_backward_argument_errors():
         ops.scan_backward_f32(img, cap, [5, 5, 5], torch.zeros(4, 2, device="cuda"), "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
     with pytest.raises(ValueError):
         ops.scan_backward_f32(img, cap, [5, 9, 5], torch.zeros(4, 3, device="cuda"), "t2i", "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    # the kernels are bounded by the batch's true longest caption (96 words), not by the padded width
     with pytest.raises(ValueError):
-        ops.scan_backward_f32(img, torch.zeros(3, 100, 64, device="cuda"), [5, 5, 5], torch.zeros(4, 3, device="cuda"), "i2t",
+        ops.scan_backward_f32(img, torch.zeros(3, 100, 64, device="cuda"), [5, 100, 5], torch.zeros(4, 3, device="cuda"), "i2t",
                               "clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    wide = torch.randn(3, 100, 64, device="cuda")
+    wide[:, 5:] = 0
+    g = torch.randn(4, 3, device="cuda")
+    im = torch.nn.functional.normalize(torch.randn(4, 36, 64, device="cuda"), dim=-1)
+    d_im_w, d_cap_w = ops.scan_backward_f32(im, wide, [5, 5, 5], g, "i2t", "clipped_l2norm", "LogSumExp", 4.0, 6.0)
+    d_im_n, d_cap_n = ops.scan_backward_f32(im, wide[:, :5].contiguous(), [5, 5, 5], g, "i2t", "clipped_l2norm", "LogSumExp", 4.0, 6.0)
+    assert d_cap_w.shape == (3, 100, 64) and torch.equal(d_cap_w[:, :5], d_cap_n) and not d_cap_w[:, 5:].any()
+    assert torch.equal(d_im_w, d_im_n)
+    assert torch.equal(ops.scan_scores_f32(im, wide, [5, 5, 5], "i2t", "clipped_l2norm", "LogSumExp", 4.0, 6.0),
+                       ops.scan_scores_f32(im, wide[:, :5].contiguous(), [5, 5, 5], "i2t", "clipped_l2norm", "LogSumExp", 4.0, 6.0))
     with pytest.raises(ValueError):
         ops.scan_backward_f32(img, cap, [5, 5, 5], torch.zeros(4, 3, device="cuda"), "t2i", "l1norm", "LogSumExp", 9.0, 6.0)
 
