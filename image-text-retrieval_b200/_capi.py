@@ -44,6 +44,7 @@ SIGNATURES = {
     "itr_scan_epilogue_f32": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p, _l, _p]),
     "itr_scan_t2i_affinity_debug": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "itr_scan_t2i_profile": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _l, _p, _i, _p]),
+    "itr_scan_t2i_pair_profile": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _l, _p, _p]),
     "itr_tc_mma_microbench": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "itr_tc_mma2_microbench": (_i, [_i, _i, _i, _i, _i, _i, _p, _p]),
     "itr_hinge_fwd_bwd_f32": (_i, [_p, _l, _i, _f, _i, _p, _p, _l, _p]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libitr_b200.so")
-SOURCES = ["simt_kernels.cu", "scan_bwd.cu", "scan_t2i_tc.cu", "tc_microbench2.cu", "plan.cpp"]
+SOURCES = ["simt_kernels.cu", "scan_bwd.cu", "scan_t2i_tc.cu", "scan_t2i_tc2.cu", "tc_microbench2.cu", "plan.cpp"]
 HEADERS = ["common.cuh", "scan_f32.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "itr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -38,15 +38,31 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Every source is compiled to its own object (in parallel), then linked into the shared library."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libitr_b200.so (exit {})".format(res.returncode))
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    with tempfile.TemporaryDirectory(prefix="itr_b200_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.splitext(src)[0] + ".o")
+            cmd = [_nvcc()] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            return obj, subprocess.run(cmd, capture_output=True, text=True)
+        with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+            results = list(pool.map(compile_one, SOURCES))
+        for obj, res in results:
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed compiling {} (exit {})".format(os.path.basename(obj), res.returncode))
+        link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC"] + \
+               [obj for obj, _ in results] + ["-o", LIB]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed linking libitr_b200.so (exit {})".format(res.returncode))
     return LIB
 
 

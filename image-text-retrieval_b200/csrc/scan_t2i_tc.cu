@@ -797,8 +797,27 @@ static int require_sm100() {
 }  // namespace tc
 }  // namespace itr
 
+namespace itr {
+namespace tc2 {
+// CTA-pair form of the fused kernel (scan_t2i_tc2.cu)
+int launch_tc2(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
+               const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
+               float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, void* stream, long long* prof);
+}  // namespace tc2
+}  // namespace itr
+
 using namespace itr;
 using namespace itr::tc;
+
+// ITR_B200_SCORE_KERNEL=single selects the one-CTA kernel of round 1 (A/B measurements); default: the CTA-pair kernel
+static bool use_pair_kernel() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("ITR_B200_SCORE_KERNEL");
+    cached = (e && e[0] == 's') ? 0 : 1;
+  }
+  return cached == 1;
+}
 
 extern "C" int itr_scan_pack_words_bf16(const float* captions, int n_cap, int lmax, int d, const int32_t* row_meta,
                                         int n_tiles, uint16_t* words_bf16, float* row_wnorm, void* stream) {
@@ -907,8 +926,25 @@ extern "C" int itr_scan_t2i_scores_bf16(const uint16_t* images_bf16, const void*
   ITR_REQUIRE(((uintptr_t)images_bf16 & 15) == 0 && ((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)gram_pack & 15) == 0 &&
               ((uintptr_t)row_meta & 15) == 0 && ((uintptr_t)row_wnorm & 15) == 0, "itr_scan_t2i_scores_bf16: buffers must be 16-byte aligned");
   if (n_img <= 0 || n_tiles <= 0) return ITR_OK;
+  if (use_pair_kernel()) {
+    int rc = require_sm100();
+    if (rc) return rc;
+    return tc2::launch_tc2(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
+                           lambda_softmax, lambda_lse, scores, ld_scores, stream, nullptr);
+  }
   return launch_tc(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
                    lambda_softmax, lambda_lse, scores, ld_scores, nullptr, 0, 0, stream);
+}
+
+extern "C" int itr_scan_t2i_pair_profile(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                                         const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                                         int n_tiles, float* scores, int64_t ld_scores, int64_t* counters, void* stream) {
+  ITR_REQUIRE(images_bf16 && gram_pack && words_bf16 && row_meta && row_wnorm && scores && counters, "itr_scan_t2i_pair_profile: null pointer");
+  if (n_img <= 0 || n_tiles <= 0) return ITR_OK;
+  int rc = require_sm100();
+  if (rc) return rc;
+  return tc2::launch_tc2(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, ITR_NORM_CLIPPED_L2, ITR_AGG_LSE,
+                         9.f, 6.f, scores, ld_scores, stream, reinterpret_cast<long long*>(counters));
 }
 
 extern "C" int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,

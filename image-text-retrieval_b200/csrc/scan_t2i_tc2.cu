@@ -1,0 +1,661 @@
+// SCAN text-to-image cross-attention scores on Blackwell tensor cores, CTA-PAIR form (sm_100a only).
+//
+// Same mathematics and the same epilogue as scan_t2i_tc.cu (read its header first); what changes is the MMA:
+// two CTAs on the two SMs of a TPC form a cluster and run ONE `tcgen05.mma.cta_group::2` per K step with
+// M = 256: CTA r of the pair supplies word tile 2*mp + r (128 rows of A) and HALF of the image tile (72 of the
+// 144 region rows of B, i.e. two of its four images); the hardware exchanges the B halves, and each CTA ends up
+// with its own 128 x 144 accumulator in its own tensor memory.  Why (profiles/r02/mma2_microbench.txt):
+//   * a tcgen05.mma costs its issuer ~115 clk whatever its size (max(115, N/2 + 45) in SS mode) and the pair form
+//     costs the same 117 clk for twice the work, so the per-SM issue work halves (64 main + 12 Gram instructions
+//     per TWO items) and the MMA side drops from ~8.7K to ~4K clk per item, below the epilogue;
+//   * each SM stages 25 KB per K block instead of 34 KB (its B half is 9 KB): the L2 -> SMEM operand stream of the
+//     image tiles halves and the ring holds 7 stages instead of 5 in the same shared memory.
+// Replaces xattn_score_t2i + func_attention + cosine_similarity (itr/modalmodule/Objectives.py:329-372, 421-476,
+// 10-15) for raw_feature_norm in {clipped_l2norm, l2norm} and every agg_func.
+//
+// Roles per CTA (20 warps, as before): warp 0 TMA producer (both CTAs; the peer's loads complete on the LEADER's
+// `full` barrier), warp 1 main MMA issuer (leader only), warp 2 TMEM allocator (both) + Gram MMA issuer (leader
+// only, also cta_group::2: M = 256, N = 48, each CTA holds 24 of the 48 rows of every Gram pack), warp 3 aux
+// loader (both), warps 4-19 epilogue (both).  Barriers that gate the leader's issuers collect arrivals from both
+// CTAs (the peer arrives through the cluster-mapped address); barriers the tensor pipe signals are multicast to
+// both CTAs with one tcgen05.commit.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace itr {
+namespace tc2 {
+
+using namespace itr::tc;
+
+constexpr int R = ITR_REGIONS;                 // 36
+constexpr int IMGS = ITR_TILE_IMAGES;          // 4
+constexpr int BLOCK_M = ITR_TILE_WORDS;        // 128 word rows per CTA (UMMA M = 256 across the pair)
+constexpr int BLOCK_N = IMGS * R;              // 144
+constexpr int HALF_N = BLOCK_N / 2;            // 72 region rows of B staged by each CTA
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int D = ITR_EMBED;                   // 1024
+constexpr int K_BLOCKS = D / BLOCK_K;          // 16
+constexpr int STAGES = 7;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2; // 16384
+constexpr int B_BYTES = HALF_N * BLOCK_K * 2;  // 9216
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 25600 (1024-aligned: SWIZZLE_128B tiles)
+constexpr int GRAM_N = 48;
+constexpr int GRAM_BYTES = ITR_GRAM_BYTES;     // 4752 per image in global memory (fp16 48x48 + 36 fp32)
+constexpr int GH_BYTES = GRAM_N * GRAM_N;      // 2304 = 24 rows x 48 k x 2 bytes: this CTA's half of one Gram pack
+constexpr int G_LBO = 128, G_SBO = 768;
+constexpr int AUX_GRAM = IMGS * GH_BYTES;      // 9216
+constexpr int AUX_META = BLOCK_M * 16;         // 2048
+constexpr int AUX_WNORM = BLOCK_M * 4;         // 512
+constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 11776
+constexpr int XCH_FLOATS = 4 * 4 * 40;
+constexpr int ACC_PITCH = BLOCK_N;             // two accumulators [0,144) and [144,288)
+constexpr int U_BASE = 2 * ACC_PITCH;          // four Gram products at 288 + 48 g
+__host__ __device__ constexpr int park_col(int g) { return g == 0 ? 0 : 16 * ((36 * g + 15) / 16); }   // 0, 48, 80, 112
+constexpr int TMEM_COLS = 512;
+constexpr int BAND = 32;                       // word-tile PAIRS (64 tiles, 16 MB) kept L2-resident while images stream
+constexpr int NUM_THREADS = 640;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 16;
+
+constexpr int SMEM_STAGES = 0;
+constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
+constexpr int SMEM_XCH = SMEM_AUX + 2 * AUX_BYTES;
+constexpr int SMEM_BARS = SMEM_XCH + XCH_FLOATS * 4;
+constexpr int NUM_BARS = 2 * STAGES + 18;
+constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
+constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
+static_assert(STAGE_BYTES % 1024 == 0 && SMEM_AUX % 16 == 0 && SMEM_BARS % 8 == 0, "alignment");
+
+// kind::f16 instruction descriptors, M = 256 across the CTA pair: D=f32, A=B=bf16 (main) / fp16 (Gram), K-major
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t IDESC_GRAM = (1u << 4) | ((uint32_t)(GRAM_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+// ---------------------------------------------------------------------------- cluster / pair PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// In a cluster of two, the shared-memory windows of the CTAs differ in one address bit (bit 24 = rank): clearing it
+// turns the address of an object of this CTA into the shared::cluster address of the same object in the leader.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+// arrive on the LEADER's copy of the barrier at `bar` (an address in this CTA's layout)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+// wait on a barrier of this CTA whose arrivals may come from the peer CTA
+__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cl(bar, parity, 0u)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cl(bar, parity, 20000u)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_cl_t(uint32_t bar, uint32_t parity, long long& acc, const bool on) {
+  if (!on) { mbar_wait_cl(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait_cl(bar, parity);
+  acc += clock64() - t0;
+}
+// TMA tile load of one CTA of a pair: the bytes complete on the LEADER's barrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once every tcgen05 operation issued so far has completed
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// ... on the issuing (leader) CTA's barrier only
+__device__ __forceinline__ void umma2_commit_local(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------- tile schedule
+// Work unit = (band of BAND consecutive word-tile PAIRS, image tile n); a CTA pair takes units u = pair, pair + #pairs, ...
+// and walks the band against the SAME image tile (see scan_t2i_tc.cu: an image tile comes from HBM once per band,
+// the band stays L2-resident).
+struct Schedule {
+  int n_wp, n_it, n_bands, last_band;
+  __device__ Schedule(int n_wp_, int n_it_) : n_wp(n_wp_), n_it(n_it_) {
+    n_bands = (n_wp + BAND - 1) / BAND;
+    last_band = n_wp - (n_bands - 1) * BAND;
+  }
+  __device__ int units() const { return n_bands * n_it; }
+};
+struct ItemIter {
+  const Schedule& s;
+  int u, step, m, n, left;      // m = word-tile PAIR index
+  __device__ ItemIter(const Schedule& s_, int first, int step_) : s(s_), u(first), step(step_) { open(); }
+  __device__ void open() {
+    if (u < s.units()) {
+      const int band = u / s.n_it;
+      n = u - band * s.n_it;
+      m = band * BAND;
+      left = (band == s.n_bands - 1) ? s.last_band : BAND;
+    }
+  }
+  __device__ bool valid() const { return u < s.units(); }
+  __device__ void next() {
+    ++m;
+    if (--left == 0) { u += step; open(); }
+  }
+};
+
+struct Params {
+  const uint8_t* gram_pack;    // [n_img][GRAM_BYTES]
+  const int4* row_meta;        // [n_wt*128]
+  const float* row_wnorm;      // [n_wt*128]
+  int n_img, n_wt, n_wp, n_it; // n_wp = ceil(n_wt / 2): the peer's tile of the last pair may not exist
+  int clipped, agg;
+  float c_sm, c_lse, inv_lse;
+  float* scores; long long ld;
+  long long* prof;             // optional [cluster][2][16] cycle counters (PROF instantiation)
+};
+
+template <bool MAXOP>
+__device__ __forceinline__ float seg_total(float x, const bool (&p)[5], int seg_hi) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    float y = __shfl_up_sync(0xffffffffu, x, 1 << s);
+    if (p[s]) x = MAXOP ? fmaxf(x, y) : x + y;
+  }
+  return __shfl_sync(0xffffffffu, x, seg_hi);
+}
+
+struct Carry {
+  float P, D, wnorm;
+  int cap, seg, n_words, img, b;
+  bool valid, img_ok, live;
+};
+
+template <bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  // logical warp index: 0-3 control, 4-19 epilogue; the control warpgroup is the LAST one physically (measured best,
+  // scan_t2i_tc.cu).  The shift is a multiple of 4: TMEM lane quarter and warpgroup alignment are preserved.
+  const int warp = (int)((threadIdx.x >> 5) + EPI_WARP0) % (NUM_THREADS / 32);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const uint32_t bar0 = sbase + SMEM_BARS;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };                          // leader: 2 producer arrivals + both CTAs' bytes
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };              // both (multicast commit)
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 0 + b); };      // both (multicast commit)
+  auto loaded_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };     // leader: 32 epilogue warps
+  auto afull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };      // local
+  auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };     // local
+  auto eready_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 8 + g); };     // leader: 8 epilogue warps
+  auto uready_bar = [&](int g) { return bar0 + 8u * (2 * STAGES + 12 + g); };    // both (multicast commit)
+  auto gfree_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 16 + b); };     // leader (local commit)
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMEM_TMEMPTR);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_words) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_imgs) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1); mbar_init(loaded_bar(b), 2 * NUM_EPI_WARPS); mbar_init(gfree_bar(b), 1);
+      mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS);
+    }
+    for (int g = 0; g < IMGS; ++g) { mbar_init(eready_bar(g), 8); mbar_init(uready_bar(g), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SMEM_TMEMPTR), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer's barriers are initialised before anybody arrives on them remotely
+  tc_fence_after();
+  if (*tmem_ptr_smem != 0u) __trap();      // the pair owns both SMs: the allocation starts at column 0
+  constexpr uint32_t tmem_base = 0u;
+
+  constexpr bool prof_on = PROF;
+  const Schedule sched(p.n_wp, p.n_it);
+  const int first = (int)(blockIdx.x >> 1);
+  const int step = (int)(gridDim.x >> 1);
+  long long* prof = PROF ? p.prof + ((size_t)(blockIdx.x >> 1) * 2 + rank) * 16 : nullptr;
+
+  if (warp < EPI_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ==============================
+    int stage = 0; uint32_t phase = 0;
+    long long w_empty = 0; const long long t_begin = prof_on ? clock64() : 0;
+    for (ItemIter item(sched, first, step); item.valid(); item.next()) {
+      const int row_w = (2 * item.m + (int)rank) * BLOCK_M;            // rows past the tensor are zero-filled
+      const int row_i = item.n * BLOCK_N + (int)rank * HALF_N;
+#pragma unroll 1
+      for (int kb = 0; kb < K_BLOCKS; ++kb) {
+        mbar_wait_sleep_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
+        const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES, fb = full_bar(stage);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);             // its own arrival + the bytes of BOTH CTAs
+          else mbar_arrive_leader(fb);
+          tma_load_2d_pair(sa, &map_words, fb, kb * BLOCK_K, row_w);
+          tma_load_2d_pair(sa + A_BYTES, &map_imgs, fb, kb * BLOCK_K, row_i);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (prof_on && lane == 0) { prof[0] = clock64() - t_begin; prof[1] = w_empty; }
+  } else if (warp == 1) {
+    // =============================== main MMA issuer (leader only) =========================
+    if (leader) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      long long w_tempty = 0, w_full = 0; const long long t_begin = prof_on ? clock64() : 0;
+      const uint64_t adesc0 = umma_desc_sw128(sbase + SMEM_STAGES);
+      const uint64_t bdesc0 = umma_desc_sw128(sbase + SMEM_STAGES + A_BYTES);
+      for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
+        // accumulator b = it & 1 (in both CTAs) is reusable once every epilogue warp of BOTH CTAs has item it-2 in
+        // registers and the Gram MMAs of item it-2, which read the numerators parked in it, have completed
+        const int ab = it & 1;
+        const uint32_t tacc = tmem_base + ab * ACC_PITCH;
+        mbar_wait_cl_t(loaded_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
+        mbar_wait_sleep_t(gfree_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < K_BLOCKS; ++kb) {
+          mbar_wait_cl_t(full_bar(stage), phase, w_full, prof_on);
+          tc_fence_after();
+          const uint64_t soff = (uint64_t)((uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4));
+          const uint64_t adesc = adesc0 + soff, bdesc = bdesc0 + soff;
+          if (elect_one()) {
+            umma2_bf16(tacc, adesc, bdesc, IDESC, (uint32_t)kb);
+            umma2_bf16(tacc, adesc + 2, bdesc + 2, IDESC, 1u);
+            umma2_bf16(tacc, adesc + 4, bdesc + 4, IDESC, 1u);
+            umma2_bf16(tacc, adesc + 6, bdesc + 6, IDESC, 1u);
+            umma2_commit_both(empty_bar(stage));
+            if (kb == K_BLOCKS - 1) umma2_commit_both(tfull_bar(ab));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (prof_on && lane == 0) { prof[2] = clock64() - t_begin; prof[3] = w_tempty; prof[4] = w_full; prof[5] = it; }
+    }
+  } else if (warp == 2) {
+    // =============================== Gram MMA issuer (leader only) =========================
+    // U_g = e_g (G_g - I) for the image's column group in BOTH CTAs: A = the parked fp16 numerators (each CTA's own
+    // tensor memory), B = the image's Gram pack, rows [0,24) from the leader's copy and [24,48) from the peer's
+    if (leader) {
+      int it = 0;
+      uint32_t used[IMGS] = {0u, 0u, 0u, 0u};
+      for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
+        const int n = item.n;
+        const int b = it & 1;
+        mbar_wait_sleep(afull_bar(b), (it >> 1) & 1);      // the leader's half; the peer's is ordered by its eready arrivals
+        const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
+#pragma unroll
+        for (int g = 0; g < IMGS; ++g) {
+          if (n * IMGS + g >= p.n_img) continue;
+          mbar_wait_cl(eready_bar(g), used[g]++ & 1);
+          tc_fence_after();
+          const uint32_t te = tmem_base + b * ACC_PITCH + park_col(g);
+          const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
+          const uint64_t gdesc = umma_desc_nosw(aux + g * GH_BYTES, G_LBO, G_SBO);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < GRAM_N / UMMA_K; ++k)
+              umma2_f16_ts(tu, te + 8 * k, gdesc + (uint64_t)((2 * G_LBO * k) >> 4), IDESC_GRAM, k != 0);
+            umma2_commit_both(uready_bar(g));
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma2_commit_local(gfree_bar(b));
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== aux loader (both CTAs) ================================
+    int it = 0;
+    for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
+      const int m = 2 * item.m + (int)rank, n = item.n;
+      const int b = it & 1;
+      mbar_wait_sleep(aempty_bar(b), ((it >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        const int n_valid = min(IMGS, p.n_img - n * IMGS);
+        const bool word_ok = m < p.n_wt;
+        const uint32_t aux = sbase + SMEM_AUX + b * AUX_BYTES;
+        mbar_expect_tx(afull_bar(b), n_valid * GH_BYTES + (word_ok ? AUX_META + AUX_WNORM : 0));
+        for (int g = 0; g < n_valid; ++g)
+          bulk_load(aux + g * GH_BYTES, p.gram_pack + (size_t)(n * IMGS + g) * GRAM_BYTES + rank * GH_BYTES, GH_BYTES, afull_bar(b));
+        if (word_ok) {
+          bulk_load(aux + AUX_GRAM, p.row_meta + (size_t)m * BLOCK_M, AUX_META, afull_bar(b));
+          bulk_load(aux + AUX_GRAM + AUX_META, p.row_wnorm + (size_t)m * BLOCK_M, AUX_WNORM, afull_bar(b));
+        }
+      }
+      __syncwarp();
+    }
+  }
+  } else {
+    // =============================== epilogue (both CTAs) ==================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp & 3;
+    const int g = (warp - EPI_WARP0) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t tu = tmem_base + U_BASE + g * GRAM_N + lane_sel;
+    const uint32_t tpark0 = tmem_base + park_col(g) + lane_sel;
+    float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
+    uint32_t used = 0u;
+    long long w_tfull = 0, w_afull = 0, w_uready = 0; const long long t_begin = prof_on ? clock64() : 0;
+    Carry c;
+    uint32_t hvp[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) hvp[k] = 0u;
+    c.live = false; c.valid = false; c.img_ok = false; c.P = c.D = c.wnorm = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
+
+    auto phase_b = [&]() {
+      if (c.img_ok) {
+        // the Gram issuer commits uready[g] for every existing image, whether or not this CTA's word tile exists
+        mbar_wait_sleep_t(uready_bar(g), used++ & 1, w_uready, prof_on);
+        tc_fence_after();
+      }
+      if (c.valid) {
+        const int seg_lo = c.seg & 0xff, seg_hi = (c.seg >> 8) & 0xff;
+        const bool long_tile = (c.seg >> 16) & 1;
+        float q0 = 0.f, q1 = 0.f, Zsum;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t Uh[18];
+          TMEM_LD_X16U(tu + 18 * h, Uh, 0);
+          TMEM_LD_X2U(tu + 18 * h + 16, Uh, 16);
+          if (h == 1) TMEM_LD_X1F(tu + 36, Zsum);
+          tmem_ld_wait();
+#pragma unroll
+          for (int cidx = 0; cidx < 9; ++cidx) {
+            float2 ef = unpack_f16x2(hvp[9 * h + cidx]);
+            q0 = fmaf(ef.x, __uint_as_float(Uh[2 * cidx]), q0); q1 = fmaf(ef.y, __uint_as_float(Uh[2 * cidx + 1]), q1);
+          }
+        }
+        const float Qf = c.D + (q0 + q1);
+        const float rj = c.P / fmaxf(c.wnorm * sqrtf(fmaxf(Qf, 0.f)), 1e-8f * Zsum);
+        bool pr[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
+        float v = (p.agg == ITR_AGG_LSE) ? ex2f(rj * p.c_lse) : rj;
+        if (c.cap < 0) v = (p.agg == ITR_AGG_MAX) ? -INFINITY : 0.f;
+        float tot;
+        if (!long_tile) {
+          tot = (p.agg == ITR_AGG_MAX) ? seg_total<true>(v, pr, seg_hi) : seg_total<false>(v, pr, seg_hi);
+        } else {
+          float* x = xch + 36;
+          tot = (p.agg == ITR_AGG_MAX) ? warp_max(v) : warp_sum(v);
+          named_bar_sync(1 + g, 128);
+          if (lane == 0) x[q * 40] = tot;
+          named_bar_sync(1 + g, 128);
+          float t0 = x[0], t1 = x[40], t2 = x[80], t3 = x[120];
+          tot = (p.agg == ITR_AGG_MAX) ? fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) : (t0 + t1) + (t2 + t3);
+        }
+        if (p.agg == ITR_AGG_LSE) tot = lg2f(tot) * p.inv_lse;
+        if (p.agg == ITR_AGG_MEAN) tot = tot / (float)c.n_words;
+        const bool writer = long_tile ? (row == 0) : (lane == seg_lo);
+        if (writer && c.cap >= 0) p.scores[(size_t)c.img * p.ld + c.cap] = tot;
+      }
+      if (c.live) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(aempty_bar(c.b));
+      }
+    };
+
+    int it = 0;
+    for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
+      const int n = item.n;
+      const int m = 2 * item.m + (int)rank;
+      const bool word_ok = m < p.n_wt;
+      const int b = it & 1;
+      mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
+      const uint8_t* aux = smem + SMEM_AUX + b * AUX_BYTES;
+      int4 meta = make_int4(-1, 0, lane | (lane << 8), 0);
+      float wnorm = 0.f;
+      if (word_ok) {
+        meta = reinterpret_cast<const int4*>(aux + AUX_GRAM)[row];
+        wnorm = reinterpret_cast<const float*>(aux + AUX_GRAM + AUX_META)[row];
+      }
+      const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
+      const bool long_tile = (meta.z >> 16) & 1;
+      const int img = n * IMGS + g;
+      const bool img_ok = img < p.n_img;
+      const bool valid = img_ok && word_ok;
+
+      const uint32_t tacc = tmem_base + b * ACC_PITCH + lane_sel;
+      mbar_wait_sleep_t(tfull_bar(b), (it >> 1) & 1, w_tfull, prof_on);
+      tc_fence_after();
+      float A[R];
+      TMEM_LD_X32(tacc + g * R, A, 0);
+      TMEM_LD_X4(tacc + g * R + 32, A, 32);
+
+      phase_b();
+
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(loaded_bar(b));
+
+      uint32_t hv[18];
+#pragma unroll
+      for (int k = 0; k < 18; ++k) hv[k] = 0u;
+      float P = 0.f, Dd = 0.f;
+      if (valid) {
+        bool pr[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
+        const float shift = -fabsf(p.c_sm);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float E[R / 2];
+#pragma unroll
+          for (int k = 0; k < R / 2; ++k) {
+            float a = p.clipped ? fmaxf(A[18 * h + k], 0.1f * A[18 * h + k]) : A[18 * h + k];
+            E[k] = a * a;
+          }
+          if (!long_tile) {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
+          } else {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) E[k] = warp_sum(E[k]);
+            named_bar_sync(1 + g, 128);
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < R / 2; ++k) xch[q * 40 + k] = E[k];
+            }
+            named_bar_sync(1 + g, 128);
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) E[k] = (xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]);
+          }
+          float smin = E[0];
+#pragma unroll
+          for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
+          const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && meta.x >= 0);
+          if (!exact) {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) {
+              const float raw = A[18 * h + k];
+              const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
+              const float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
+              E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) {
+              const float raw = A[18 * h + k];
+              const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
+              const float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
+              E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
+            }
+          }
+#pragma unroll
+          for (int cidx = 0; cidx < 9; ++cidx) hv[9 * h + cidx] = pack_f16x2(E[2 * cidx], E[2 * cidx + 1]);
+        }
+      }
+
+      // park(t): e(t) as fp16 (K padded 36 -> 48 with zeros) in the group's own columns of the accumulator it came from,
+      // wake the (leader's) Gram issuer.  An image that exists is signalled by BOTH CTAs, word tile or not.
+      if (img_ok) {
+        const uint32_t tpark = tpark0 + b * ACC_PITCH;
+        uint32_t z[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        TMEM_ST_X16(tpark, hv, 0);
+        TMEM_ST_X2(tpark + 16, hv, 16);
+        TMEM_ST_X4(tpark + 18, z, 0);
+        TMEM_ST_X2(tpark + 22, z, 4);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(eready_bar(g));
+      }
+#pragma unroll
+      for (int k = 0; k < 18; ++k) hvp[k] = hv[k];
+      c.P = P; c.D = Dd; c.wnorm = wnorm; c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w;
+      c.img = img; c.b = b; c.valid = valid; c.img_ok = img_ok; c.live = true;
+    }
+    phase_b();
+    if (prof_on && lane == 0 && q == 0) {
+      long long* o = prof + 6 + g * 2;
+      o[0] = w_tfull + w_afull; o[1] = w_uready;
+      if (g == 0) { prof[14] = clock64() - t_begin; prof[15] = w_afull; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // nobody frees tensor memory or exits while the peer can still signal or read it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ITR_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !ptr) return fail(ITR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cached = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  *fn = cached;
+  return ITR_OK;
+}
+
+// 2-D bf16 tensor [rows][1024], box = [box_rows][64], 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ITR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ITR_OK;
+}
+
+template <bool PROF>
+static int launch(const CUtensorMap& map_w, const CUtensorMap& map_i, const Params& p, cudaStream_t stream) {
+  auto kern = scan_t2i_tc2_kernel<PROF>;
+  ITR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+  int dev = 0, sms = 0;
+  ITR_CHECK_CUDA(cudaGetDevice(&dev));
+  ITR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // how many CTA pairs the device keeps resident at once (a static round-robin schedule must not be split in waves)
+  static int max_pairs = -1;
+  if (max_pairs < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sms & ~1)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_ALLOC;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2; }
+    max_pairs = n < sms / 2 ? n : sms / 2;
+  }
+  const long long units = (long long)((p.n_wp + BAND - 1) / BAND) * p.n_it;
+  const int pairs = (int)(units < max_pairs ? units : max_pairs);
+  kern<<<2 * pairs, NUM_THREADS, SMEM_ALLOC, stream>>>(map_w, map_i, p);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+int launch_tc2(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
+               const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
+               float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, void* stream, long long* prof) {
+  CUtensorMap map_w, map_i;
+  int rc = make_map(&map_w, words_bf16, (uint64_t)n_tiles * BLOCK_M, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&map_i, images_bf16, (uint64_t)n_img * R, HALF_N);
+  if (rc) return rc;
+  Params p{};
+  p.gram_pack = reinterpret_cast<const uint8_t*>(gram_pack);
+  p.row_meta = reinterpret_cast<const int4*>(row_meta);
+  p.row_wnorm = row_wnorm;
+  p.n_img = n_img; p.n_wt = n_tiles; p.n_wp = (n_tiles + 1) / 2; p.n_it = (n_img + IMGS - 1) / IMGS;
+  p.clipped = (feature_norm == ITR_NORM_CLIPPED_L2); p.agg = agg;
+  p.c_sm = lambda_softmax * 1.4426950408889634f;
+  p.c_lse = lambda_lse * 1.4426950408889634f;
+  p.inv_lse = 0.6931471805599453f / lambda_lse;
+  p.scores = scores; p.ld = ld_scores; p.prof = prof;
+  if ((long long)p.n_wp * p.n_it >= (1ll << 31))
+    return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tile pairs exceed the 2^31 scheduler range; split the call", (long long)p.n_wp * p.n_it);
+  return prof ? launch<true>(map_w, map_i, p, as_stream(stream)) : launch<false>(map_w, map_i, p, as_stream(stream));
+}
+
+}  // namespace tc2
+}  // namespace itr

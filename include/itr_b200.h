@@ -126,7 +126,9 @@ int itr_scan_backward_f32(const float* images, const float* gram, const float* c
  * 3. itr_scan_prep_images_bf16: rounds regions to bf16 and writes, per image, the Gram pack of the
  *    rounded regions (ITR_GRAM_BYTES): G = V V^T with the off-diagonal part in fp16, laid out as the
  *    SMEM B operand of a 128x48x48 tcgen05.mma, and the diagonal in fp32.
- * 4. itr_scan_t2i_scores_bf16: persistent TMA -> tcgen05.mma -> TMEM epilogue kernel.
+ * 4. itr_scan_t2i_scores_bf16: persistent TMA -> tcgen05.mma -> TMEM epilogue kernel; two CTAs per cluster run one
+ *    tcgen05.mma.cta_group::2 (M = 256) per K step (csrc/scan_t2i_tc2.cu).  ITR_B200_SCORE_KERNEL=single in the
+ *    environment selects the one-CTA kernel of csrc/scan_t2i_tc.cu instead (A/B measurements).
  */
 int itr_scan_plan_max_tiles(const int32_t* cap_lens_host, int n_cap);
 int itr_scan_plan_words(const int32_t* cap_lens_host, int n_cap, int32_t* row_meta_host, int* n_tiles);
@@ -171,6 +173,11 @@ int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_img, const ui
 int itr_scan_t2i_profile(const uint16_t* images_bf16, const void* gram_pack, int n_img,
                          const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                          int n_tiles, float* scores, int64_t ld_scores, int64_t* counters, int mode, void* stream);
+
+/* Same counters for the CTA-pair kernel (csrc/scan_t2i_tc2.cu): counters[pair][rank][16] int64, pair < #SMs / 2. */
+int itr_scan_t2i_pair_profile(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                              const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                              int n_tiles, float* scores, int64_t ld_scores, int64_t* counters, void* stream);
 
 /* Tuning: cycles until `n_issuers` warps have each pushed `iters` tcgen05.mma (M=128, K=16, kind::f16) through the
  * tensor pipe of one CTA, on `n_ctas` CTAs; see csrc/scan_t2i_tc.cu.  cycles[n_ctas]. */
