@@ -91,32 +91,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 // In a cluster of two, the shared-memory windows of the CTAs differ in one address bit (bit 24 = rank): clearing it
 // turns the address of an object of this CTA into the shared::cluster address of the same object in the leader.
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
-// arrive on the LEADER's copy of the barrier at `bar` (an address in this CTA's layout)
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
-}
-// wait on a barrier of this CTA whose arrivals may come from the peer CTA
-__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cl(bar, parity, 0u)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cl(bar, parity, 20000u)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-__device__ __forceinline__ void mbar_wait_cl_t(uint32_t bar, uint32_t parity, long long& acc, const bool on) {
-  if (!on) { mbar_wait_cl(bar, parity); return; }
-  const long long t0 = clock64();
-  mbar_wait_cl(bar, parity);
-  acc += clock64() - t0;
+// arrive on the LEADER's copy of the barrier at `bar` (an address in this CTA's layout).  The leader takes the plain
+// shared::cta form; the peer the shared::cluster form WITHOUT .release.cluster: measured (profiles/r02/
+// role_profile_pair_v1_slow.txt), a cluster-scope release costs the arriving warp ~850 clk per arrive, and nothing needs
+// it here -- the tcgen05.ld / tcgen05.st the arrival publishes have completed (wait::ld / wait::st) before it is issued.
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, bool leader) {
+  if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  else asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 // TMA tile load of one CTA of a pair: the bytes complete on the LEADER's barrier (peer bit of the address cleared)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -219,7 +200,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
   const bool leader = rank == 0;
 
   const uint32_t bar0 = sbase + SMEM_BARS;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };                          // leader: 2 producer arrivals + both CTAs' bytes
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };                          // leader: its producer's arrival + both CTAs' bytes
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };              // both (multicast commit)
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 0 + b); };      // both (multicast commit)
   auto loaded_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };     // leader: 32 epilogue warps
@@ -235,7 +216,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_imgs) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1); mbar_init(loaded_bar(b), 2 * NUM_EPI_WARPS); mbar_init(gfree_bar(b), 1);
       mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), NUM_EPI_WARPS);
@@ -274,8 +255,10 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         mbar_wait_sleep_t(empty_bar(stage), phase ^ 1, w_empty, prof_on);
         const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES, fb = full_bar(stage);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);             // its own arrival + the bytes of BOTH CTAs
-          else mbar_arrive_leader(fb);
+          // one arrival per phase: the leader's, which expects the bytes of BOTH CTAs.  The peer cannot run a phase
+          // ahead: it refills stage s only after the MMAs that consumed it completed (its own `empty`, multicast by
+          // the leader), i.e. after the leader's `full` phase for that stage is over.
+          if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);
           tma_load_2d_pair(sa, &map_words, fb, kb * BLOCK_K, row_w);
           tma_load_2d_pair(sa + A_BYTES, &map_imgs, fb, kb * BLOCK_K, row_i);
         }
@@ -297,12 +280,12 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         // registers and the Gram MMAs of item it-2, which read the numerators parked in it, have completed
         const int ab = it & 1;
         const uint32_t tacc = tmem_base + ab * ACC_PITCH;
-        mbar_wait_cl_t(loaded_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
+        mbar_wait_sleep_t(loaded_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
         mbar_wait_sleep_t(gfree_bar(ab), ((it >> 1) & 1) ^ 1, w_tempty, prof_on);
         tc_fence_after();
 #pragma unroll 1
         for (int kb = 0; kb < K_BLOCKS; ++kb) {
-          mbar_wait_cl_t(full_bar(stage), phase, w_full, prof_on);
+          mbar_wait_sleep_t(full_bar(stage), phase, w_full, prof_on);
           tc_fence_after();
           const uint64_t soff = (uint64_t)((uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4));
           const uint64_t adesc = adesc0 + soff, bdesc = bdesc0 + soff;
@@ -335,7 +318,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
 #pragma unroll
         for (int g = 0; g < IMGS; ++g) {
           if (n * IMGS + g >= p.n_img) continue;
-          mbar_wait_cl(eready_bar(g), used[g]++ & 1);
+          mbar_wait_sleep(eready_bar(g), used[g]++ & 1);
           tc_fence_after();
           const uint32_t te = tmem_base + b * ACC_PITCH + park_col(g);
           const uint32_t tu = tmem_base + U_BASE + g * GRAM_N;
@@ -478,7 +461,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(loaded_bar(b));
+      if (lane == 0) mbar_arrive_leader(loaded_bar(b), leader);
 
       uint32_t hv[18];
 #pragma unroll
@@ -550,7 +533,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_leader(eready_bar(g));
+        if (lane == 0) mbar_arrive_leader(eready_bar(g), leader);
       }
 #pragma unroll
       for (int k = 0; k < 18; ++k) hvp[k] = hv[k];
