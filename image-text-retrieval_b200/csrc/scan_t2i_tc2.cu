@@ -41,7 +41,7 @@ constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int D = ITR_EMBED;                   // 1024
 constexpr int K_BLOCKS = D / BLOCK_K;          // 16
-constexpr int STAGES = 7;
+constexpr int STAGES = 5;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2; // 16384
 constexpr int B_BYTES = HALF_N * BLOCK_K * 2;  // 9216
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 25600 (1024-aligned: SWIZZLE_128B tiles)
@@ -54,6 +54,10 @@ constexpr int AUX_META = BLOCK_M * 16;         // 2048
 constexpr int AUX_WNORM = BLOCK_M * 4;         // 512
 constexpr int AUX_BYTES = AUX_GRAM + AUX_META + AUX_WNORM;   // 11776
 constexpr int XCH_FLOATS = 4 * 4 * 40;
+// per-epilogue-warp scratch for the l2norm denominators: a^2 of the warp's 32 word rows x 36 regions.  Pitch 36 floats:
+// the 8-byte row stores are 2-way bank conflicted (a conflict-free pitch of 38 does not leave room for 5 stages).
+constexpr int SQ_PITCH = 36;
+constexpr int SQ_WARP_FLOATS = 32 * SQ_PITCH;
 constexpr int ACC_PITCH = BLOCK_N;             // two accumulators [0,144) and [144,288)
 constexpr int U_BASE = 2 * ACC_PITCH;          // four Gram products at 288 + 48 g
 __host__ __device__ constexpr int park_col(int g) { return g == 0 ? 0 : 16 * ((36 * g + 15) / 16); }   // 0, 48, 80, 112
@@ -66,13 +70,14 @@ constexpr int NUM_EPI_WARPS = 16;
 constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_XCH = SMEM_AUX + 2 * AUX_BYTES;
-constexpr int SMEM_BARS = SMEM_XCH + XCH_FLOATS * 4;
+constexpr int SMEM_SQ = SMEM_XCH + XCH_FLOATS * 4;
+constexpr int SMEM_BARS = SMEM_SQ + NUM_EPI_WARPS * SQ_WARP_FLOATS * 4;
 constexpr int NUM_BARS = 2 * STAGES + 18;
 constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
-static_assert(STAGE_BYTES % 1024 == 0 && SMEM_AUX % 16 == 0 && SMEM_BARS % 8 == 0, "alignment");
+static_assert(STAGE_BYTES % 1024 == 0 && SMEM_AUX % 16 == 0 && SMEM_SQ % 16 == 0 && SMEM_BARS % 8 == 0, "alignment");
 
 // kind::f16 instruction descriptors, M = 256 across the CTA pair: D=f32, A=B=bf16 (main) / fp16 (Gram), K-major
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -126,6 +131,17 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
 // ... on the issuing (leader) CTA's barrier only
 __device__ __forceinline__ void umma2_commit_local(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// explicit shared-space accesses (a pointer derived from the manually aligned dynamic-SMEM base is a GENERIC pointer to
+// the compiler: it would emit LD.E / ST.E with address translation instead of LDS / STS)
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
 }
 
 // ---------------------------------------------------------------------------- tile schedule
@@ -186,7 +202,7 @@ struct Carry {
   bool valid, img_ok, live;
 };
 
-template <bool PROF>
+template <bool PROF, bool CLIPPED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -367,6 +383,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     const uint32_t tu = tmem_base + U_BASE + g * GRAM_N + lane_sel;
     const uint32_t tpark0 = tmem_base + park_col(g) + lane_sel;
     float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + g * 4 * 40;
+    const uint32_t sq = sbase + SMEM_SQ + (uint32_t)(warp - EPI_WARP0) * (SQ_WARP_FLOATS * 4);      // shared-space address
     uint32_t used = 0u;
     long long w_tfull = 0, w_afull = 0, w_uready = 0; const long long t_begin = prof_on ? clock64() : 0;
     Carry c;
@@ -456,69 +473,113 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       TMEM_LD_X32(tacc + g * R, A, 0);
       TMEM_LD_X4(tacc + g * R + 32, A, 32);
 
-      phase_b();
-
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(loaded_bar(b), leader);
+
+      // ---- A(t), first half: l2norm denominators.  S[c][k] = sum over the caption's words of a^2: every lane writes the
+      // a^2 of its word row to the warp's scratch, then lanes 0..17 walk the 32 rows, two regions each, restarting at
+      // every caption end (a caption never straddles a warp) and leaving lambda*log2e / sqrt(S) -- the softmax scale the
+      // whole caption shares -- in the caption's LAST row: ~175 instructions and ~70 shared-memory operations instead of
+      // 36 x (6 shuffles + 5 adds) of segmented warp scans, and one rsqrt per (caption, region) instead of per (word, region).
+      bool exact = false;                       // some denominator is ~0: take the reference's exact 1/(sqrt(S)+1e-8)
+      if (valid && !long_tile) {
+        const uint32_t myrow = sq + (uint32_t)lane * (SQ_PITCH * 4);
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+          const float a0 = CLIPPED ? fmaxf(A[k], 0.1f * A[k]) : A[k];
+          const float a1 = CLIPPED ? fmaxf(A[k + 1], 0.1f * A[k + 1]) : A[k + 1];
+          sts_f2(myrow + 4 * k, a0 * a0, a1 * a1);
+        }
+        __syncwarp();
+        const uint32_t endmask = __ballot_sync(0xffffffffu, lane == seg_hi);
+        const uint32_t realmask = __ballot_sync(0xffffffffu, lane == seg_hi && meta.x >= 0);
+        bool tiny = false;
+        if (lane < R / 2) {
+          const uint32_t col = sq + 8u * (uint32_t)lane;
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+          for (int j0 = 0; j0 < 32; j0 += 8) {        // eight independent loads in flight, then the dependent adds
+            float2 v[8];                              // (rolled over the four row blocks: the epilogue is i-cache bound)
+            const uint32_t blk = col + (uint32_t)(j0 * SQ_PITCH * 4);
+            const uint32_t ends = endmask >> j0, reals = realmask >> j0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = lds_f2(blk + (uint32_t)(j * SQ_PITCH * 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc.x += v[j].x; acc.y += v[j].y;
+              if ((ends >> j) & 1u) {
+                const float r0 = rsqf(fmaxf(acc.x, 1e-36f)), r1 = rsqf(fmaxf(acc.y, 1e-36f));
+                if ((reals >> j) & 1u) tiny = tiny || fmaxf(r0, r1) > 31622.f;      // S < 1e-9
+                sts_f2(blk + (uint32_t)(j * SQ_PITCH * 4), p.c_sm * r0, p.c_sm * r1);
+                acc = make_float2(0.f, 0.f);
+              }
+            }
+          }
+        }
+        __syncwarp();                                // the scale stores are visible to the whole warp (a vote is no fence)
+        exact = __any_sync(0xffffffffu, tiny);
+      }
+
+      // ---- B(t-1): finish the previous item.  Its Gram product was issued when the last of the eight warps parked,
+      // ~2K clk ago by now, behind whatever main MMAs were queued: nobody waits for it here.
+      phase_b();
 
       uint32_t hv[18];
 #pragma unroll
       for (int k = 0; k < 18; ++k) hv[k] = 0u;
       float P = 0.f, Dd = 0.f;
       if (valid) {
-        bool pr[5];
-#pragma unroll
-        for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
         const float shift = -fabsf(p.c_sm);
+        const float inv_c = 1.0f / p.c_sm;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float E[R / 2];
-#pragma unroll
-          for (int k = 0; k < R / 2; ++k) {
-            float a = p.clipped ? fmaxf(A[18 * h + k], 0.1f * A[18 * h + k]) : A[18 * h + k];
-            E[k] = a * a;
-          }
+          float E[R / 2];                       // softmax scales lambda*log2e/sqrt(S[c][k]) of this half's regions
           if (!long_tile) {
+            const uint32_t tot = sq + (uint32_t)(seg_hi * SQ_PITCH + 18 * h) * 4u;
 #pragma unroll
-            for (int k = 0; k < R / 2; ++k) E[k] = seg_total<false>(E[k], pr, seg_hi);
+            for (int k = 0; k < R / 2; k += 2) {
+              const float2 t = lds_f2(tot + 4 * k);
+              E[k] = t.x; E[k + 1] = t.y;
+            }
           } else {
 #pragma unroll
-            for (int k = 0; k < R / 2; ++k) E[k] = warp_sum(E[k]);
+            for (int k = 0; k < R / 2; ++k) {
+              const float a = CLIPPED ? fmaxf(A[18 * h + k], 0.1f * A[18 * h + k]) : A[18 * h + k];
+              E[k] = warp_sum(a * a);
+            }
             named_bar_sync(1 + g, 128);
             if (lane == 0) {
 #pragma unroll
               for (int k = 0; k < R / 2; ++k) xch[q * 40 + k] = E[k];
             }
             named_bar_sync(1 + g, 128);
+            bool tiny = false;
 #pragma unroll
-            for (int k = 0; k < R / 2; ++k) E[k] = (xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]);
+            for (int k = 0; k < R / 2; ++k) {
+              const float r = rsqf(fmaxf((xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]), 1e-36f));
+              tiny = tiny || r > 31622.f;
+              E[k] = p.c_sm * r;
+            }
+            exact = __any_sync(0xffffffffu, tiny && meta.x >= 0);
           }
-          float smin = E[0];
+          if (exact) {
+            // lambda / (sqrt(S) + 1e-8) = t / (1 + 1e-8 / sqrt(S)) with t = lambda / sqrt(S)   (rare: kept out of the main loop)
 #pragma unroll
-          for (int k = 1; k < R / 2; ++k) smin = fminf(smin, E[k]);
-          const bool exact = __any_sync(0xffffffffu, smin < 1e-9f && meta.x >= 0);
-          if (!exact) {
+            for (int k = 0; k < R / 2; ++k) E[k] = __fdividef(E[k], fmaf(1e-8f * inv_c, E[k], 1.0f));
+          }
 #pragma unroll
-            for (int k = 0; k < R / 2; ++k) {
-              const float raw = A[18 * h + k];
-              const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
-              const float e = ex2f(fmaf(a, p.c_sm * rsqf(E[k]), shift));
-              E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < R / 2; ++k) {
-              const float raw = A[18 * h + k];
-              const float a = p.clipped ? fmaxf(raw, 0.1f * raw) : raw;
-              const float e = ex2f(fmaf(a, __fdividef(p.c_sm, sqrtf(E[k]) + 1e-8f), shift));
-              E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
-            }
+          for (int k = 0; k < R / 2; ++k) {
+            const float raw = A[18 * h + k];
+            const float a = CLIPPED ? fmaxf(raw, 0.1f * raw) : raw;
+            const float e = ex2f(fmaf(a, E[k], shift));
+            E[k] = e; P = fmaf(e, raw, P); Dd = fmaf(e, e, Dd);
           }
 #pragma unroll
           for (int cidx = 0; cidx < 9; ++cidx) hv[9 * h + cidx] = pack_f16x2(E[2 * cidx], E[2 * cidx + 1]);
         }
+        if (!long_tile) __syncwarp();           // every lane has read its caption's scales before the next item's stores
       }
 
       // park(t): e(t) as fp16 (K padded 36 -> 48 with zeros) in the group's own columns of the accumulator it came from,
@@ -591,9 +652,9 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t 
   return ITR_OK;
 }
 
-template <bool PROF>
+template <bool PROF, bool CLIPPED>
 static int launch(const CUtensorMap& map_w, const CUtensorMap& map_i, const Params& p, cudaStream_t stream) {
-  auto kern = scan_t2i_tc2_kernel<PROF>;
+  auto kern = scan_t2i_tc2_kernel<PROF, CLIPPED>;
   ITR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
   int dev = 0, sms = 0;
   ITR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -637,7 +698,9 @@ int launch_tc2(const uint16_t* images_bf16, const void* gram_pack, int n_img, co
   p.scores = scores; p.ld = ld_scores; p.prof = prof;
   if ((long long)p.n_wp * p.n_it >= (1ll << 31))
     return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tile pairs exceed the 2^31 scheduler range; split the call", (long long)p.n_wp * p.n_it);
-  return prof ? launch<true>(map_w, map_i, p, as_stream(stream)) : launch<false>(map_w, map_i, p, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (prof) return launch<true, true>(map_w, map_i, p, st);       // the profile entry point always runs clipped_l2norm
+  return p.clipped ? launch<false, true>(map_w, map_i, p, st) : launch<false, false>(map_w, map_i, p, st);
 }
 
 }  // namespace tc2
