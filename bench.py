@@ -37,6 +37,8 @@ CONFIG = dict(name="SCAN", cross_attn="t2i", raw_feature_norm="clipped_l2norm", 
               lambda_lse=6.0, lambda_softmax=9.0, margin=0.2, max_violation=True, measure="cosine")
 METRIC = "image-caption pair scores/sec (SCAN t2i COCO-5K eval)"
 R, D = 36, 1024
+# the dominant kernel: the CTA-pair (tcgen05 cta_group::2) score kernel unless ITR_B200_SCORE_KERNEL=single selects round 1's
+SCORE_KERNEL = "scan_t2i_tc_kernel" if os.environ.get("ITR_B200_SCORE_KERNEL", "").startswith("s") else "scan_t2i_tc2_kernel"
 
 
 def measured_traffic(n_img, n_cap, world):
@@ -44,7 +46,7 @@ def measured_traffic(n_img, n_cap, world):
     for rnd in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
         path = os.path.join(ROOT, "profiles", rnd, "ncu_traffic.json")
         if os.path.exists(path):
-            rec = json.load(open(path)).get("scan_t2i_tc_kernel", {}).get("{}x{}@{}".format(n_img, n_cap, world))
+            rec = json.load(open(path)).get(SCORE_KERNEL, {}).get("{}x{}@{}".format(n_img, n_cap, world))
             if rec:
                 return rec["dram_bytes_read"] + rec["dram_bytes_write"]
     return None
@@ -63,6 +65,9 @@ def parse():
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5, 6],
                     help="BASELINE.json config to measure; 5 (default) is the headline the driver runs; "
                          "6 = SCAN training step (fwd + bwd, batch 128), not a BASELINE config")
+    ap.add_argument("--rank-mode", default="fused", choices=["fused", "matrix"],
+                    help="device step: 'fused' ranks inside the score kernel (no score matrix), 'matrix' writes the matrix "
+                         "and ranks it with the rank kernels (round 1); the other mode is timed briefly and reported too")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-caps", type=int, default=CPU_SAMPLE[1])
     return ap.parse_args()
@@ -361,17 +366,43 @@ def main():
     # per-step device breakdown: [start, images prepared (+ all-gathered), captions packed, scores done, ranks merged]
     marks = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
 
-    def step(i=None):
+    kern_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+
+    class TimedStats(sharding.FusedScanStats):
+        """FusedScanStats with CUDA events around the counting launch (the dominant kernel of the fused step)."""
+        slot = None
+
+        def count(self, block, thr_row, thr_col, cap_offset):
+            if self.slot is not None:
+                kern_ev[self.slot][0].record()
+            res = super().count(block, thr_row, thr_col, cap_offset)
+            if self.slot is not None:
+                kern_ev[self.slot][1].record()
+            return res
+
+    def step(i=None, mode=None):
+        mode = mode or args.rank_mode
         mark = (lambda k: marks[i][k].record()) if i is not None else (lambda k: None)
         mark(0)
         pi = ops.prepare_images_sharded(images, None, dev)      # each rank preps 1/N of the images + NCCL all-gather
         mark(1)
         pc = ops.prepare_captions(captions, ln_local)
         mark(2)
-        ops.scan_t2i_scores_bf16(pi, pc, CONFIG["raw_feature_norm"], CONFIG["agg_func"], CONFIG["lambda_softmax"],
-                                 CONFIG["lambda_lse"], out=scores)
-        mark(3)
-        out = sharding.sharded_ranks(scores, lo, n_cap, None, 5)
+        if mode == "matrix":
+            if i is not None:
+                kern_ev[i][0].record()
+            ops.scan_t2i_scores_bf16(pi, pc, CONFIG["raw_feature_norm"], CONFIG["agg_func"], CONFIG["lambda_softmax"],
+                                     CONFIG["lambda_lse"], out=scores)
+            if i is not None:
+                kern_ev[i][1].record()
+            mark(3)
+            out = sharding.sharded_ranks(scores, lo, n_cap, None, 5)
+        else:
+            # ground-truth pre-pass (<1 % of the items) -> threshold all-reduce -> counting pass -> one all-gather
+            stats = TimedStats(pi, pc, CONFIG["raw_feature_norm"], CONFIG["agg_func"], CONFIG["lambda_softmax"], CONFIG["lambda_lse"])
+            stats.slot = i
+            mark(3)
+            out = sharding.sharded_ranks(stats.block(), lo, n_cap, None, 5, stats)
         mark(4)
         return out
 
@@ -390,14 +421,35 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     seg = [float(np.mean([m[k].elapsed_time(m[k + 1]) for m in marks])) for k in range(4)]
-    kern_ms = torch.tensor([seg[2]], device=dev)
+    kern_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))], device=dev)
     seg_ms = torch.tensor(seg, device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(seg_ms, op=dist.ReduceOp.MAX)
-    breakdown = dict(zip(["prep_images" + ("+all_gather" if world > 1 else ""), "pack_captions", "score_kernel",
-                          "rank_kernels" + ("+exchange" if world > 1 else "")], [round(x, 3) for x in seg_ms.tolist()]))
+    if args.rank_mode == "matrix":
+        names = ["prep_images" + ("+all_gather" if world > 1 else ""), "pack_captions", "score_kernel",
+                 "rank_kernels" + ("+exchange" if world > 1 else "")]
+    else:
+        names = ["prep_images" + ("+all_gather" if world > 1 else ""), "pack_captions", "host_setup",
+                 "gt_prepass+score_count_kernel" + ("+exchange" if world > 1 else "")]
+    breakdown = dict(zip(names, [round(x, 3) for x in seg_ms.tolist()]))
+    breakdown["score_kernel_alone"] = round(kern_ms.item(), 3)
+    # the other ranking mode, timed briefly on the same inputs
+    other = "matrix" if args.rank_mode == "fused" else "fused"
+    for _ in range(2):
+        out_other = step(mode=other)
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(3):
+        out_other = step(mode=other)
+    o1.record()
+    barrier()
+    other_ms = torch.tensor([o0.elapsed_time(o1) / 3], device=dev)
+    if world > 1:
+        dist.all_reduce(other_ms, op=dist.ReduceOp.MAX)
+    same_ranks = all(torch.equal(a, b) for a, b in zip(out, out_other))
     ms_per_step = elapsed_ms.item() / args.steps
     value = n_img * n_cap / (ms_per_step * 1e-3)
     i2t_ranks, _, t2i_ranks, _ = out
@@ -485,22 +537,27 @@ def main():
         "config": {"workload": "SCAN t2i clipped_l2norm LogSumExp (lambda_lse 6, lambda_softmax 9), COCO-5K shape: "
                                "{} images x {} captions ({} words), captions sharded over {} GPU(s)".format(n_img, n_cap, sum_words, world),
                    "n_img": n_img, "n_cap": n_cap, "sum_words": sum_words, "parallelism": "caption-shard x{}".format(world),
-                   "l2_policy": "inputs larger than L2 (bf16 operands {:.0f} MB + {:.0f} MB score block per GPU)".format(
-                       (n_img * R * D * 2 + n_tiles * 128 * D * 2) / 1e6, n_img * (hi - lo) * 4 / 1e6),
-                   "step": "prep(cast,pack,gram" + (", image shards all-gathered over NCCL" if world > 1 else "") + ") + tcgen05 scores + rank kernels" + (" + rank exchange" if world > 1 else "")},
+                   "l2_policy": "inputs larger than L2 (bf16 operands {:.0f} MB per GPU{})".format(
+                       (n_img * R * D * 2 + n_tiles * 128 * D * 2) / 1e6,
+                       "" if args.rank_mode == "fused" else " + {:.0f} MB score block".format(n_img * (hi - lo) * 4 / 1e6)),
+                   "step": "prep(cast,pack,gram" + (", image shards all-gathered over NCCL" if world > 1 else "") + ") + " +
+                           ("ground-truth pre-pass + tcgen05 scores with the ranking in the epilogue (no score matrix)" if args.rank_mode == "fused"
+                            else "tcgen05 scores + rank kernels") + (" + rank exchange" if world > 1 else "")},
         "eval_wall_ms": {"device": ms_per_step, "e2e": e2e_s.item() * 1e3},
         "device_breakdown_ms": breakdown,
+        "rank_mode": {"timed": args.rank_mode, "ms_per_step": ms_per_step, "other": other, "other_ms_per_step": other_ms.item(),
+                      "identical_ranks": bool(same_ranks)},
         "recall_check": {"i2t_r1": r1, "t2i_r1": r1_t, "e2e_rsum": res["rsum"]},
-        "roofline": {"bound": "tensor", "kernel": "scan_t2i_tc_kernel", "achieved": achieved, "peak": pk["tflops"],
+        "roofline": {"bound": "tensor", "kernel": SCORE_KERNEL, "achieved": achieved, "peak": pk["tflops"],
                      "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": measured_traffic(n_img, n_cap, world),
-                     "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01/ncu_traffic.json); algorithmic minimum {:.2f} GB".format(
+                     "traffic_unit": "DRAM bytes per launch (ncu, profiles/*/ncu_traffic.json); algorithmic minimum {:.2f} GB".format(
                          (n_img * R * D * 2 + sum_words_local * D * 2 + n_img * (hi - lo) * 4) / 1e9),
                      "peak_source": pk["src"],
                      "kernel_ms": kern_ms.item(), "algorithmic_flop_per_launch": f_alg,
                      "kernel_share_of_step": kern_ms.item() / ms_per_step},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s.item() * 1e3},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 5 * args.steps,      # fused: prep, pack, gt pre-pass, threshold un-key, score+count; matrix: prep, pack, scores, thresholds, counts
         "clocks": clocks,
     }
     if dropin is not None:

@@ -148,19 +148,28 @@ __device__ __forceinline__ void sts_f2(uint32_t addr, float x, float y) {
 // Work unit = (band of BAND consecutive word-tile PAIRS, image tile n); a CTA pair takes units u = pair, pair + #pairs, ...
 // and walks the band against the SAME image tile (see scan_t2i_tc.cu: an image tile comes from HBM once per band,
 // the band stays L2-resident).
-struct Schedule {
+// With an explicit item list (the ground-truth pre-pass of the fused evaluation) a unit is one listed
+// (word-tile pair, image tile) item.
+template <bool LIST>
+struct ScheduleT {
   int n_wp, n_it, n_bands, last_band;
-  __device__ Schedule(int n_wp_, int n_it_) : n_wp(n_wp_), n_it(n_it_) {
+  const int2* items; int n_items;
+  __device__ ScheduleT(int n_wp_, int n_it_, const int2* items_, int n_items_) : n_wp(n_wp_), n_it(n_it_), items(items_), n_items(n_items_) {
     n_bands = (n_wp + BAND - 1) / BAND;
     last_band = n_wp - (n_bands - 1) * BAND;
   }
-  __device__ int units() const { return n_bands * n_it; }
+  __device__ int units() const { return LIST ? n_items : n_bands * n_it; }
 };
-struct ItemIter {
-  const Schedule& s;
+template <bool LIST>
+struct ItemIterT {
+  const ScheduleT<LIST>& s;
   int u, step, m, n, left;      // m = word-tile PAIR index
-  __device__ ItemIter(const Schedule& s_, int first, int step_) : s(s_), u(first), step(step_) { open(); }
+  __device__ ItemIterT(const ScheduleT<LIST>& s_, int first, int step_) : s(s_), u(first), step(step_) { open(); }
   __device__ void open() {
+    if (LIST) {
+      if (u < s.n_items) { const int2 e = s.items[u]; m = e.x; n = e.y; left = 1; }
+      return;
+    }
     if (u < s.units()) {
       const int band = u / s.n_it;
       n = u - band * s.n_it;
@@ -182,9 +191,19 @@ struct Params {
   int n_img, n_wt, n_wp, n_it; // n_wp = ceil(n_wt / 2): the peer's tile of the last pair may not exist
   int clipped, agg;
   float c_sm, c_lse, inv_lse;
-  float* scores; long long ld;
+  float* scores; long long ld; // MODE_SCORES: required; MODE_COUNT: optional (NULL = the matrix is never written)
   long long* prof;             // optional [cluster][2][16] cycle counters (PROF instantiation)
+  // fused evaluation (i2t / t2i ranking, evaluation.py:156-222): caption c of this launch is global caption cap_offset + c,
+  // whose ground-truth image is (cap_offset + c) / cpi
+  const int2* items; int n_items;          // MODE_GT: the (word-tile pair, image tile) items that hold a ground-truth pair
+  int cap_offset, cpi;
+  float* thr_col;                          // [n_cap]  MODE_GT: written; MODE_COUNT: read (NaN = no ground-truth image here)
+  unsigned int* thr_row_key;               // [n_img]  MODE_GT: atomicMax of the orderable key of the ground-truth scores
+  const float* thr_row;                    // [n_img]  MODE_COUNT
+  int* cnt_col; int* cnt_row;              // MODE_COUNT: += #scores strictly above the threshold
+  unsigned long long* best_col; unsigned long long* best_row;   // MODE_COUNT: atomicMax of (orderable score << 32 | ~index)
 };
+constexpr int MODE_SCORES = 0, MODE_GT = 1, MODE_COUNT = 2;
 
 template <bool MAXOP>
 __device__ __forceinline__ float seg_total(float x, const bool (&p)[5], int seg_hi) {
@@ -202,7 +221,7 @@ struct Carry {
   bool valid, img_ok, live;
 };
 
-template <bool PROF, bool CLIPPED>
+template <bool PROF, bool CLIPPED, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_imgs, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -252,7 +271,9 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
   constexpr uint32_t tmem_base = 0u;
 
   constexpr bool prof_on = PROF;
-  const Schedule sched(p.n_wp, p.n_it);
+  using Schedule = ScheduleT<MODE == MODE_GT>;
+  using ItemIter = ItemIterT<MODE == MODE_GT>;
+  const Schedule sched(p.n_wp, p.n_it, MODE == MODE_GT ? p.items : nullptr, MODE == MODE_GT ? p.n_items : 0);
   const int first = (int)(blockIdx.x >> 1);
   const int step = (int)(gridDim.x >> 1);
   long long* prof = PROF ? p.prof + ((size_t)(blockIdx.x >> 1) * 2 + rank) * 16 : nullptr;
@@ -437,7 +458,31 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         if (p.agg == ITR_AGG_LSE) tot = lg2f(tot) * p.inv_lse;
         if (p.agg == ITR_AGG_MEAN) tot = tot / (float)c.n_words;
         const bool writer = long_tile ? (row == 0) : (lane == seg_lo);
-        if (writer && c.cap >= 0) p.scores[(size_t)c.img * p.ld + c.cap] = tot;
+        if (writer && c.cap >= 0) {
+          if (MODE == MODE_SCORES) {
+            p.scores[(size_t)c.img * p.ld + c.cap] = tot;
+          } else if (MODE == MODE_GT) {
+            // ground-truth pre-pass: the same arithmetic on the same packed rows as the counting pass, so the
+            // thresholds are bit-identical to the scores it will compare them with
+            if ((p.cap_offset + c.cap) / p.cpi == c.img) {
+              p.thr_col[c.cap] = tot;
+              atomicMax(p.thr_row_key + c.img, orderable(tot));
+            }
+          } else {
+            if (p.scores) p.scores[(size_t)c.img * p.ld + c.cap] = tot;
+            // rank = #scores strictly above the ground-truth score; a score can be the arg-max of its row / column only
+            // if it is not below that score, so the packed keys are built on the rare path only
+            const float tc = p.thr_col[c.cap], tr = p.thr_row[c.img];
+            if (!(tot < tc)) {
+              if (tot > tc) atomicAdd(p.cnt_col + c.cap, 1);
+              atomicMax(p.best_col + c.cap, ((unsigned long long)orderable(tot) << 32) | (unsigned)(~(unsigned)c.img));
+            }
+            if (!(tot < tr)) {
+              if (tot > tr) atomicAdd(p.cnt_row + c.img, 1);
+              atomicMax(p.best_row + c.img, ((unsigned long long)orderable(tot) << 32) | (unsigned)(~(unsigned)(p.cap_offset + c.cap)));
+            }
+          }
+        }
       }
       if (c.live) {
         tc_fence_before();
@@ -483,7 +528,10 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       // every caption end (a caption never straddles a warp) and leaving lambda*log2e / sqrt(S) -- the softmax scale the
       // whole caption shares -- in the caption's LAST row: ~175 instructions and ~70 shared-memory operations instead of
       // 36 x (6 shuffles + 5 adds) of segmented warp scans, and one rsqrt per (caption, region) instead of per (word, region).
-      bool exact = false;                       // some denominator is ~0: take the reference's exact 1/(sqrt(S)+1e-8)
+      // lambda / (sqrt(S) + 1e-8), the reference's l2norm + softmax temperature (utils.py:11-15), as t / (1 + 1e-8 r) with
+      // r = rsqrt(S), t = lambda r: computed per (caption, region), so it costs nothing to take the exact form always --
+      // and the result of a caption does not depend on which captions share its warp.
+      const float eps_c = 1e-8f;
       if (valid && !long_tile) {
         const uint32_t myrow = sq + (uint32_t)lane * (SQ_PITCH * 4);
 #pragma unroll
@@ -494,8 +542,6 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         }
         __syncwarp();
         const uint32_t endmask = __ballot_sync(0xffffffffu, lane == seg_hi);
-        const uint32_t realmask = __ballot_sync(0xffffffffu, lane == seg_hi && meta.x >= 0);
-        bool tiny = false;
         if (lane < R / 2) {
           const uint32_t col = sq + 8u * (uint32_t)lane;
           float2 acc = make_float2(0.f, 0.f);
@@ -503,7 +549,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
           for (int j0 = 0; j0 < 32; j0 += 8) {        // eight independent loads in flight, then the dependent adds
             float2 v[8];                              // (rolled over the four row blocks: the epilogue is i-cache bound)
             const uint32_t blk = col + (uint32_t)(j0 * SQ_PITCH * 4);
-            const uint32_t ends = endmask >> j0, reals = realmask >> j0;
+            const uint32_t ends = endmask >> j0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = lds_f2(blk + (uint32_t)(j * SQ_PITCH * 4));
 #pragma unroll
@@ -511,15 +557,14 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
               acc.x += v[j].x; acc.y += v[j].y;
               if ((ends >> j) & 1u) {
                 const float r0 = rsqf(fmaxf(acc.x, 1e-36f)), r1 = rsqf(fmaxf(acc.y, 1e-36f));
-                if ((reals >> j) & 1u) tiny = tiny || fmaxf(r0, r1) > 31622.f;      // S < 1e-9
-                sts_f2(blk + (uint32_t)(j * SQ_PITCH * 4), p.c_sm * r0, p.c_sm * r1);
+                sts_f2(blk + (uint32_t)(j * SQ_PITCH * 4), __fdividef(p.c_sm * r0, fmaf(eps_c, r0, 1.0f)),
+                       __fdividef(p.c_sm * r1, fmaf(eps_c, r1, 1.0f)));
                 acc = make_float2(0.f, 0.f);
               }
             }
           }
         }
-        __syncwarp();                                // the scale stores are visible to the whole warp (a vote is no fence)
-        exact = __any_sync(0xffffffffu, tiny);
+        __syncwarp();                                // the scale stores are visible to the whole warp
       }
 
       // ---- B(t-1): finish the previous item.  Its Gram product was issued when the last of the eight warps parked,
@@ -532,7 +577,6 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       float P = 0.f, Dd = 0.f;
       if (valid) {
         const float shift = -fabsf(p.c_sm);
-        const float inv_c = 1.0f / p.c_sm;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float E[R / 2];                       // softmax scales lambda*log2e/sqrt(S[c][k]) of this half's regions
@@ -555,19 +599,11 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
               for (int k = 0; k < R / 2; ++k) xch[q * 40 + k] = E[k];
             }
             named_bar_sync(1 + g, 128);
-            bool tiny = false;
 #pragma unroll
             for (int k = 0; k < R / 2; ++k) {
               const float r = rsqf(fmaxf((xch[k] + xch[40 + k]) + (xch[80 + k] + xch[120 + k]), 1e-36f));
-              tiny = tiny || r > 31622.f;
-              E[k] = p.c_sm * r;
+              E[k] = __fdividef(p.c_sm * r, fmaf(eps_c, r, 1.0f));
             }
-            exact = __any_sync(0xffffffffu, tiny && meta.x >= 0);
-          }
-          if (exact) {
-            // lambda / (sqrt(S) + 1e-8) = t / (1 + 1e-8 / sqrt(S)) with t = lambda / sqrt(S)   (rare: kept out of the main loop)
-#pragma unroll
-            for (int k = 0; k < R / 2; ++k) E[k] = __fdividef(E[k], fmaf(1e-8f * inv_c, E[k], 1.0f));
           }
 #pragma unroll
           for (int k = 0; k < R / 2; ++k) {
@@ -652,9 +688,9 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t 
   return ITR_OK;
 }
 
-template <bool PROF, bool CLIPPED>
+template <bool PROF, bool CLIPPED, int MODE>
 static int launch(const CUtensorMap& map_w, const CUtensorMap& map_i, const Params& p, cudaStream_t stream) {
-  auto kern = scan_t2i_tc2_kernel<PROF, CLIPPED>;
+  auto kern = scan_t2i_tc2_kernel<PROF, CLIPPED, MODE>;
   ITR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
   int dev = 0, sms = 0;
   ITR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -671,22 +707,21 @@ static int launch(const CUtensorMap& map_w, const CUtensorMap& map_i, const Para
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2; }
     max_pairs = n < sms / 2 ? n : sms / 2;
   }
-  const long long units = (long long)((p.n_wp + BAND - 1) / BAND) * p.n_it;
+  const long long units = MODE == MODE_GT ? (long long)p.n_items : (long long)((p.n_wp + BAND - 1) / BAND) * p.n_it;
+  if (units <= 0) return ITR_OK;
   const int pairs = (int)(units < max_pairs ? units : max_pairs);
   kern<<<2 * pairs, NUM_THREADS, SMEM_ALLOC, stream>>>(map_w, map_i, p);
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }
 
-int launch_tc2(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
-               const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
-               float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, void* stream, long long* prof) {
-  CUtensorMap map_w, map_i;
+static int fill_params(Params& p, CUtensorMap& map_w, CUtensorMap& map_i, const uint16_t* images_bf16, const void* gram_pack,
+                       int n_img, const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm, int n_tiles,
+                       int feature_norm, int agg, float lambda_softmax, float lambda_lse) {
   int rc = make_map(&map_w, words_bf16, (uint64_t)n_tiles * BLOCK_M, BLOCK_M);
   if (rc) return rc;
   rc = make_map(&map_i, images_bf16, (uint64_t)n_img * R, HALF_N);
   if (rc) return rc;
-  Params p{};
   p.gram_pack = reinterpret_cast<const uint8_t*>(gram_pack);
   p.row_meta = reinterpret_cast<const int4*>(row_meta);
   p.row_wnorm = row_wnorm;
@@ -695,13 +730,151 @@ int launch_tc2(const uint16_t* images_bf16, const void* gram_pack, int n_img, co
   p.c_sm = lambda_softmax * 1.4426950408889634f;
   p.c_lse = lambda_lse * 1.4426950408889634f;
   p.inv_lse = 0.6931471805599453f / lambda_lse;
-  p.scores = scores; p.ld = ld_scores; p.prof = prof;
   if ((long long)p.n_wp * p.n_it >= (1ll << 31))
-    return fail(ITR_ERR_INVALID, "itr_scan_t2i_scores_bf16: %lld tile pairs exceed the 2^31 scheduler range; split the call", (long long)p.n_wp * p.n_it);
+    return fail(ITR_ERR_INVALID, "itr_scan_t2i_*_bf16: %lld tile pairs exceed the 2^31 scheduler range; split the call", (long long)p.n_wp * p.n_it);
+  return ITR_OK;
+}
+
+int launch_tc2(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
+               const int32_t* row_meta, const float* row_wnorm, int n_tiles, int feature_norm, int agg,
+               float lambda_softmax, float lambda_lse, float* scores, int64_t ld_scores, void* stream, long long* prof) {
+  CUtensorMap map_w, map_i;
+  Params p{};
+  int rc = fill_params(p, map_w, map_i, images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
+                       lambda_softmax, lambda_lse);
+  if (rc) return rc;
+  p.scores = scores; p.ld = ld_scores; p.prof = prof;
   cudaStream_t st = as_stream(stream);
-  if (prof) return launch<true, true>(map_w, map_i, p, st);       // the profile entry point always runs clipped_l2norm
-  return p.clipped ? launch<false, true>(map_w, map_i, p, st) : launch<false, false>(map_w, map_i, p, st);
+  if (prof) return launch<true, true, MODE_SCORES>(map_w, map_i, p, st);       // the profile entry point always runs clipped_l2norm
+  return p.clipped ? launch<false, true, MODE_SCORES>(map_w, map_i, p, st) : launch<false, false, MODE_SCORES>(map_w, map_i, p, st);
+}
+
+// thr_row keys (atomicMax of orderable(score); 0 = no ground-truth caption seen) -> float thresholds (-inf)
+__global__ void unkey_thresholds_kernel(const unsigned int* __restrict__ key, float* __restrict__ thr_row, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned int u = key[i];
+    thr_row[i] = u == 0u ? -INFINITY : __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+  }
+}
+
+// Ground-truth pre-pass of the fused evaluation: scores of the (image, caption) pairs with caption / cpi == image, on
+// the listed items only.  thr_col[c] = that score (NaN where the caption's image is not in [0, n_img)), thr_row[i] = the
+// best of image i's ground-truth captions among THIS launch's captions (-inf if none).
+int launch_tc2_gt(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
+                  const int32_t* row_meta, const float* row_wnorm, int n_tiles, int n_cap, const int32_t* items, int n_items,
+                  int feature_norm, int agg, float lambda_softmax, float lambda_lse, int cap_offset, int cpi,
+                  float* thr_col, float* thr_row, void* stream) {
+  CUtensorMap map_w, map_i;
+  Params p{};
+  int rc = fill_params(p, map_w, map_i, images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
+                       lambda_softmax, lambda_lse);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  p.items = reinterpret_cast<const int2*>(items); p.n_items = n_items;
+  p.cap_offset = cap_offset; p.cpi = cpi;
+  p.thr_col = thr_col;
+  p.thr_row_key = reinterpret_cast<unsigned int*>(thr_row);        // keys first, converted in place below
+  ITR_CHECK_CUDA(cudaMemsetAsync(thr_col, 0xFF, sizeof(float) * (size_t)n_cap, st));      // NaN
+  ITR_CHECK_CUDA(cudaMemsetAsync(thr_row, 0, sizeof(float) * (size_t)n_img, st));
+  rc = p.clipped ? launch<false, true, MODE_GT>(map_w, map_i, p, st) : launch<false, false, MODE_GT>(map_w, map_i, p, st);
+  if (rc) return rc;
+  unkey_thresholds_kernel<<<(n_img + 255) / 256, 256, 0, st>>>(p.thr_row_key, thr_row, n_img);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
+// Counting pass of the fused evaluation: every score is compared with its row / column threshold as it is produced;
+// the matrix itself is written only if `scores` is given.
+int launch_tc2_count(const uint16_t* images_bf16, const void* gram_pack, int n_img, const uint16_t* words_bf16,
+                     const int32_t* row_meta, const float* row_wnorm, int n_tiles, int n_cap, int feature_norm, int agg,
+                     float lambda_softmax, float lambda_lse, int cap_offset, const float* thr_col, const float* thr_row,
+                     float* scores, int64_t ld_scores, int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col,
+                     void* stream) {
+  CUtensorMap map_w, map_i;
+  Params p{};
+  int rc = fill_params(p, map_w, map_i, images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
+                       lambda_softmax, lambda_lse);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  p.scores = scores; p.ld = ld_scores;
+  p.cap_offset = cap_offset; p.cpi = 1;
+  p.thr_col = const_cast<float*>(thr_col); p.thr_row = thr_row;
+  p.cnt_row = cnt_row; p.cnt_col = cnt_col;
+  p.best_row = reinterpret_cast<unsigned long long*>(best_row); p.best_col = reinterpret_cast<unsigned long long*>(best_col);
+  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_row, 0, sizeof(int32_t) * (size_t)n_img, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, sizeof(int32_t) * (size_t)n_cap, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(best_row, 0, sizeof(uint64_t) * (size_t)n_img, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, sizeof(uint64_t) * (size_t)n_cap, st));
+  return p.clipped ? launch<false, true, MODE_COUNT>(map_w, map_i, p, st) : launch<false, false, MODE_COUNT>(map_w, map_i, p, st);
 }
 
 }  // namespace tc2
 }  // namespace itr
+
+using namespace itr;
+
+static int require_sm100_tc2() {
+  int dev = 0, major = 0;
+  ITR_CHECK_CUDA(cudaGetDevice(&dev));
+  ITR_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(ITR_ERR_UNSUPPORTED, "the tensor-core SCAN path needs an sm_100 device (found sm_%d0)", major);
+  return ITR_OK;
+}
+
+#define ITR_TC2_COMMON_CHECKS(name)                                                                                              \
+  ITR_REQUIRE(images_bf16 && gram_pack && words_bf16 && row_meta && row_wnorm, name ": null pointer");                            \
+  ITR_REQUIRE(feature_norm == ITR_NORM_CLIPPED_L2 || feature_norm == ITR_NORM_L2,                                                \
+              name ": raw_feature_norm %d is only available in the float32 path", feature_norm);                                 \
+  ITR_REQUIRE(agg >= 0 && agg <= ITR_AGG_SUM, "unknown aggfunc: %d", agg);                                                       \
+  ITR_REQUIRE(lambda_lse != 0.f || agg != ITR_AGG_LSE, name ": lambda_lse must be non-zero");                                    \
+  ITR_REQUIRE(lambda_softmax > -80.f && lambda_softmax < 80.f, name ": |lambda_softmax| must be < 80");                          \
+  ITR_REQUIRE(((uintptr_t)images_bf16 & 15) == 0 && ((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)gram_pack & 15) == 0 &&     \
+              ((uintptr_t)row_meta & 15) == 0 && ((uintptr_t)row_wnorm & 15) == 0, name ": buffers must be 16-byte aligned");    \
+  ITR_REQUIRE(n_img >= 0 && n_tiles >= 0 && n_cap >= 0 && cap_offset >= 0, name ": bad shape")
+
+extern "C" int itr_scan_t2i_gt_thresholds_bf16(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                                               const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                                               int n_tiles, int n_cap, const int32_t* items, int n_items, int feature_norm, int agg,
+                                               float lambda_softmax, float lambda_lse, int cap_offset, int caps_per_img,
+                                               float* thr_col, float* thr_row, void* stream) {
+  ITR_TC2_COMMON_CHECKS("itr_scan_t2i_gt_thresholds_bf16");
+  ITR_REQUIRE(thr_col && thr_row && (items || n_items == 0) && n_items >= 0 && caps_per_img >= 1, "itr_scan_t2i_gt_thresholds_bf16: bad arguments");
+  if (n_img == 0 && n_cap == 0) return ITR_OK;
+  int rc = require_sm100_tc2();
+  if (rc) return rc;
+  if (n_img == 0 || n_tiles == 0 || n_cap == 0) {          // nothing to score: thresholds keep their "none" values
+    cudaStream_t st = as_stream(stream);
+    if (n_cap) ITR_CHECK_CUDA(cudaMemsetAsync(thr_col, 0xFF, sizeof(float) * (size_t)n_cap, st));
+    if (n_img) {
+      ITR_CHECK_CUDA(cudaMemsetAsync(thr_row, 0, sizeof(float) * (size_t)n_img, st));
+      tc2::unkey_thresholds_kernel<<<(n_img + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned int*>(thr_row), thr_row, n_img);
+      ITR_CHECK_LAUNCH();
+    }
+    return ITR_OK;
+  }
+  return tc2::launch_tc2_gt(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, n_cap, items, n_items,
+                            feature_norm, agg, lambda_softmax, lambda_lse, cap_offset, caps_per_img, thr_col, thr_row, stream);
+}
+
+extern "C" int itr_scan_t2i_count_bf16(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                                       const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                                       int n_tiles, int n_cap, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
+                                       int cap_offset, const float* thr_col, const float* thr_row, float* scores, int64_t ld_scores,
+                                       int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col, void* stream) {
+  ITR_TC2_COMMON_CHECKS("itr_scan_t2i_count_bf16");
+  ITR_REQUIRE(thr_col && thr_row && cnt_row && cnt_col && best_row && best_col, "itr_scan_t2i_count_bf16: null pointer");
+  ITR_REQUIRE(!scores || ld_scores >= n_cap, "itr_scan_t2i_count_bf16: ld_scores < n_cap");
+  if (n_img == 0 && n_cap == 0) return ITR_OK;
+  int rc = require_sm100_tc2();
+  if (rc) return rc;
+  if (n_img == 0 || n_tiles == 0 || n_cap == 0) {
+    cudaStream_t st = as_stream(stream);
+    if (n_img) { ITR_CHECK_CUDA(cudaMemsetAsync(cnt_row, 0, 4 * (size_t)n_img, st)); ITR_CHECK_CUDA(cudaMemsetAsync(best_row, 0, 8 * (size_t)n_img, st)); }
+    if (n_cap) { ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, 4 * (size_t)n_cap, st)); ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, 8 * (size_t)n_cap, st)); }
+    return ITR_OK;
+  }
+  return tc2::launch_tc2_count(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, n_cap, feature_norm, agg,
+                               lambda_softmax, lambda_lse, cap_offset, thr_col, thr_row, scores, ld_scores, cnt_row, cnt_col,
+                               best_row, best_col, stream);
+}

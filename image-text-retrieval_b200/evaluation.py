@@ -160,6 +160,46 @@ def _scan_t2i_from(pi, caps, ln, norm, config, dev):
     return ops.scan_t2i_scores_bf16(pi, ops.prepare_captions(caps, ln, device=dev), *args)
 
 
+def _sim_function(model):
+    config = model.config
+    if config["name"] in ["CAMERA"]:
+        return model.mvm
+    return model.sim_enc if getattr(model, "sim_enc", None) is not None else model.criterion.sim
+
+
+def _tc_t2i_inputs(model, img_embs, cap_embs, ln, image_group, dev):
+    """Inputs of the fused tcgen05 SCAN t2i kernel, or None when this evaluation does not run on it.
+    Returns (prepared images, captions tensor (CUDA or pinned host), raw_feature_norm)."""
+    config = model.config
+    cal_fun = _sim_function(model)
+    norm = config.get("raw_feature_norm")
+    # decided from rank-invariant inputs (config, image shape) ...
+    tc_t2i = (cal_fun is objectives.xattn_score_t2i and objectives._precision(config) == "bf16"
+              and norm in ("clipped_l2norm", "l2norm") and ln is not None
+              and getattr(img_embs, "ndim", 0) == 3 and tuple(img_embs.shape[1:]) == (36, 1024)
+              and getattr(cap_embs, "ndim", 0) == 3 and cap_embs.shape[2] == 1024)
+    if not tc_t2i:
+        return None
+    # ... and from the caption lengths, which are rank-LOCAL when the captions are sharded: the sharded path runs
+    # collectives (image all-gather), so every rank must take the same branch -- agree on one flag first (an empty
+    # local block is fine: nothing to score, but the rank still joins the all-gather).
+    lens_ok = ln.size == 0 or (int(np.min(ln)) >= 1 and int(np.max(ln)) <= ops.TC_MAX_WORDS)
+    if image_group is not None:
+        lens_ok = ops.all_ranks_agree(lens_ok, image_group, dev)
+    if not lens_ok:
+        return None
+    caps = cap_embs if isinstance(cap_embs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cap_embs))
+    if caps.dtype != torch.float32:
+        caps = caps.float()
+    if not caps.is_cuda and not caps.is_pinned():
+        caps = _to_device(caps, dev)          # pageable host memory: staged copy of the padded array
+    if image_group is not None:
+        pi = ops.prepare_images_sharded(img_embs, image_group, dev)
+    else:
+        pi = ops.prepare_images(_to_device(img_embs, dev))
+    return pi, caps, norm
+
+
 def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False,
                 image_group=None):
     """The score matrix as a CUDA float32 tensor (n_img, n_cap); inputs host or device.
@@ -167,38 +207,16 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
     (tensor-core SCAN path only; every rank passes the full image array and its own captions)."""
     dev = _device()
     config = model.config
-    if config["name"] in ["CAMERA"]:
-        cal_fun = model.mvm
-    else:
-        cal_fun = model.sim_enc if getattr(model, "sim_enc", None) is not None else model.criterion.sim
+    cal_fun = _sim_function(model)
     n_img, n_cap = len(img_embs), len(cap_embs)
     ln = _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths)
 
     fused = cal_fun in (objectives.cosine_sim, objectives.xattn_score_t2i, objectives.xattn_score_i2t)
     with torch.no_grad():
         if fused:
-            norm = config.get("raw_feature_norm")
-            # the fused tcgen05 t2i kernel: decided from rank-invariant inputs (config, image shape) ...
-            tc_t2i = (cal_fun is objectives.xattn_score_t2i and objectives._precision(config) == "bf16"
-                      and norm in ("clipped_l2norm", "l2norm") and ln is not None
-                      and getattr(img_embs, "ndim", 0) == 3 and tuple(img_embs.shape[1:]) == (36, 1024)
-                      and getattr(cap_embs, "ndim", 0) == 3 and cap_embs.shape[2] == 1024)
-            # ... and from the caption lengths, which are rank-LOCAL when the captions are sharded: the sharded path
-            # runs collectives (image all-gather), so every rank must take the same branch -- agree on one flag first
-            # (an empty local block is fine: nothing to score, but the rank still joins the all-gather).
-            lens_ok = tc_t2i and (ln.size == 0 or (int(np.min(ln)) >= 1 and int(np.max(ln)) <= ops.TC_MAX_WORDS))
-            if tc_t2i and image_group is not None:
-                lens_ok = ops.all_ranks_agree(lens_ok, image_group, dev)
-            if tc_t2i and lens_ok:
-                caps = cap_embs if isinstance(cap_embs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cap_embs))
-                if caps.dtype != torch.float32:
-                    caps = caps.float()
-                if not caps.is_cuda and not caps.is_pinned():
-                    caps = _to_device(caps, dev)          # pageable host memory: staged copy of the padded array
-                if image_group is not None:
-                    pi = ops.prepare_images_sharded(img_embs, image_group, dev)
-                else:
-                    pi = ops.prepare_images(_to_device(img_embs, dev))
+            tc = _tc_t2i_inputs(model, img_embs, cap_embs, ln, image_group, dev)
+            if tc is not None:
+                pi, caps, norm = tc
                 if n_cap == 0:
                     return torch.empty(n_img, 0, device=dev, dtype=torch.float32)
                 return _scan_t2i_from(pi, caps, ln, norm, config, dev)
@@ -216,6 +234,40 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
                 cap_block = _to_device(cap_embs[c0:c1], dev)
                 out[i0:i1, c0:c1] = cal_fun(img_block, cap_block, None if ln is None else ln[c0:c1], config)
         return out
+
+
+def fused_ranks(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False, image_group=None,
+                start=0, n_cap_total=None, caps_per_img=CAPS_PER_IMG, return_block=False):
+    """(i2t_ranks, i2t_top1, t2i_ranks, t2i_top1[, score block]) of this rank's captions against all images.
+
+    SCAN t2i on the tensor-core path ranks INSIDE the score kernel (ground-truth pre-pass + counting epilogue,
+    include/itr_b200.h "fused evaluation"): no (n_img, n_cap) matrix exists unless ``return_block``.  Captions that
+    stream from pinned host memory in several chunks keep the pipelined matrix path (the thresholds of ALL captions
+    would have to exist before the first chunk is counted, which would expose the whole PCIe gather), and so does
+    every other similarity function."""
+    from . import sharding
+    dev = _device()
+    n_img, n_cap = len(img_embs), len(cap_embs)
+    n_cap_total = n_cap if n_cap_total is None else n_cap_total
+    ln = _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths)
+    config = model.config
+    with torch.no_grad():
+        tc = _tc_t2i_inputs(model, img_embs, cap_embs, ln, image_group, dev) if _sim_function(model) is objectives.xattn_score_t2i else None
+        if tc is not None and n_cap > 0 and (tc[1].is_cuda or len(ops.host_caption_chunks(ln)) == 1):
+            pi, caps, norm = tc
+            pc = ops.prepare_captions(caps, ln, device=dev)
+            block = torch.empty(n_img, n_cap, device=dev, dtype=torch.float32) if return_block else None
+            stats = sharding.FusedScanStats(pi, pc, norm, config["agg_func"], config["lambda_softmax"],
+                                            config.get("lambda_lse", 6.0), scores_out=block)
+            out = sharding.sharded_ranks(stats.block(), start, n_cap_total, image_group, caps_per_img, stats)
+            return out + ((block,) if return_block else ())
+        if tc is not None:
+            pi, caps, norm = tc
+            block = _scan_t2i_from(pi, caps, ln, norm, config, dev) if n_cap else torch.empty(n_img, 0, device=dev)
+        else:
+            block = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths, image_group)
+    out = sharding.sharded_ranks(block, start, n_cap_total, image_group, caps_per_img)
+    return out + ((block,) if return_block else ())
 
 
 class _ValLogger(dict):
@@ -373,11 +425,11 @@ def cal_sims_and_recall(model, img_embs, cap_embs, lengths=None, shard_size=128,
                         compat_unsliced_lengths=False):
     """Fused evaluation: scores and both rankings stay on the device; only the (N,) / (5N,) rank and
     top-1 vectors come back (plus the matrix when ``return_sims``)."""
-    sims = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths)
-    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in device_ranks(sims)]
+    out = fused_ranks(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths, return_block=return_sims)
+    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in out[:4]]
     res = _recall_dict(_metrics(a), (a, b), _metrics(c), (c, d), verbose)
     if return_sims:
-        res["sims"] = sims
+        res["sims"] = out[4]
     return res
 
 

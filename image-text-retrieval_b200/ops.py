@@ -258,6 +258,8 @@ class PreparedCaptions:
     n_tiles: int
     n_cap: int
     sum_len: int
+    meta_host: np.ndarray = None  # the same row metadata on the host (the ground-truth item planner reads it)
+    plan_key: tuple = None        # identifies the packing (memoised plans)
 
 
 TC_MAX_WORDS = 128           # longest caption the fused tcgen05 t2i kernel scores (one 128-row word tile)
@@ -286,10 +288,36 @@ def plan_words_device(lengths: np.ndarray, device):
     hit = _PLAN_CACHE.pop(key, None)
     if hit is None:
         meta_host, n_tiles = plan_words(lengths)
-        hit = (torch.from_numpy(meta_host).to(device), n_tiles)
+        hit = (torch.from_numpy(meta_host).to(device), n_tiles, meta_host, key)
     _PLAN_CACHE[key] = hit                      # most recently used last
     while len(_PLAN_CACHE) > 16:
         _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    return hit
+
+
+_GT_ITEMS_CACHE = {}
+
+
+def gt_items(pc: "PreparedCaptions", cap_offset, caps_per_img, n_img):
+    """(items int32 (n_items, 2) on the device, n_items): the (word-tile pair, image tile) items of the ground-truth
+    pre-pass for this packing (csrc/plan.cpp, itr_scan_plan_gt_items), memoised next to the plan."""
+    key = (pc.plan_key, int(cap_offset), int(caps_per_img), int(n_img), str(pc.row_meta.device))
+    hit = _GT_ITEMS_CACHE.pop(key, None) if pc.plan_key is not None else None
+    if hit is None:
+        meta = pc.meta_host if pc.meta_host is not None else pc.row_meta.cpu().numpy()
+        meta = np.ascontiguousarray(meta, dtype=np.int32)
+        L = capi.lib()
+        n = capi.C.c_int(0)
+        check(L.itr_scan_plan_gt_items(meta.ctypes.data, pc.n_tiles, int(cap_offset), int(caps_per_img), int(n_img), None, 0,
+                                       capi.C.byref(n)))
+        items = np.empty((max(n.value, 1), 2), dtype=np.int32)
+        check(L.itr_scan_plan_gt_items(meta.ctypes.data, pc.n_tiles, int(cap_offset), int(caps_per_img), int(n_img),
+                                       items.ctypes.data, n.value, capi.C.byref(n)))
+        hit = (torch.from_numpy(items).to(pc.row_meta.device), n.value)
+    if pc.plan_key is not None:
+        _GT_ITEMS_CACHE[key] = hit
+        while len(_GT_ITEMS_CACHE) > 32:
+            _GT_ITEMS_CACHE.pop(next(iter(_GT_ITEMS_CACHE)))
     return hit
 
 
@@ -387,14 +415,14 @@ def prepare_captions(captions, cap_lens, device=None) -> PreparedCaptions:
     ln = lengths_to_numpy(cap_lens, n_cap)
     if n_cap and ln.max() > lmax:
         raise ValueError("caption length {} exceeds the padded width {}".format(int(ln.max()), lmax))
-    meta, n_tiles = plan_words_device(ln, device)
+    meta, n_tiles, meta_host, plan_key = plan_words_device(ln, device)
     rows = n_tiles * capi.TILE_WORDS
     words = torch.empty(rows, capi.EMBED, device=device, dtype=torch.bfloat16)
     wnorm = torch.empty(rows, device=device, dtype=torch.float32)
     with torch.cuda.device(device):
         check(capi.lib().itr_scan_pack_words_bf16(ptr(captions), n_cap, lmax, d, ptr(meta), n_tiles, ptr(words), ptr(wnorm),
                                                   stream_ptr()))
-    return PreparedCaptions(words, meta, wnorm, n_tiles, n_cap, int(ln.sum()))
+    return PreparedCaptions(words, meta, wnorm, n_tiles, n_cap, int(ln.sum()), meta_host, plan_key)
 
 
 def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, agg_func, lambda_softmax,
@@ -410,6 +438,47 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
                                                   float(lambda_softmax), float(lambda_lse), ptr(out),
                                                   out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))
     return out
+
+
+def scan_t2i_gt_thresholds(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, agg_func, lambda_softmax, lambda_lse,
+                           cap_offset=0, caps_per_img=5):
+    """Ground-truth pre-pass of the fused evaluation (itr_scan_t2i_gt_thresholds_bf16).  Returns (thr_row (n_img,),
+    thr_col (n_cap,)): thr_col[c] = score of local caption c with its own image, thr_row[i] = best score of image i with
+    its captions among THESE captions (-inf if none) -- all-reduce(MAX) it across caption shards before counting."""
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    dev = pi.images_bf16.device
+    thr_row = torch.empty(pi.n_img, device=dev, dtype=torch.float32)
+    thr_col = torch.empty(pc.n_cap, device=dev, dtype=torch.float32)
+    items, n_items = gt_items(pc, cap_offset, caps_per_img, pi.n_img)
+    with torch.cuda.device(dev):
+        check(capi.lib().itr_scan_t2i_gt_thresholds_bf16(ptr(pi.images_bf16), ptr(pi.gram_pack), pi.n_img, ptr(pc.words_bf16),
+                                                         ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, pc.n_cap, ptr(items),
+                                                         n_items, norm, agg, float(lambda_softmax), float(lambda_lse),
+                                                         int(cap_offset), int(caps_per_img), ptr(thr_col), ptr(thr_row),
+                                                         stream_ptr()))
+    return thr_row, thr_col
+
+
+def scan_t2i_count(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, agg_func, lambda_softmax, lambda_lse,
+                   thr_row, thr_col, cap_offset=0, out=None):
+    """Counting pass of the fused evaluation (itr_scan_t2i_count_bf16): the score kernel compares every score with its
+    row / column threshold as it is produced.  Returns (cnt_row i32 (n_img,), cnt_col i32 (n_cap,), best_row u64-as-i64,
+    best_col u64-as-i64) in the formats of rank_count; the score matrix is written only if `out` is given."""
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    dev = pi.images_bf16.device
+    cnt_row = torch.empty(pi.n_img, device=dev, dtype=torch.int32)
+    cnt_col = torch.empty(pc.n_cap, device=dev, dtype=torch.int32)
+    best_row = torch.empty(pi.n_img, device=dev, dtype=torch.int64)
+    best_col = torch.empty(pc.n_cap, device=dev, dtype=torch.int64)
+    if out is not None:
+        assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
+    with torch.cuda.device(dev):
+        check(capi.lib().itr_scan_t2i_count_bf16(ptr(pi.images_bf16), ptr(pi.gram_pack), pi.n_img, ptr(pc.words_bf16),
+                                                 ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, pc.n_cap, norm, agg,
+                                                 float(lambda_softmax), float(lambda_lse), int(cap_offset), ptr(thr_col),
+                                                 ptr(thr_row), ptr(out), out.stride(0) if out is not None else 0,
+                                                 ptr(cnt_row), ptr(cnt_col), ptr(best_row), ptr(best_col), stream_ptr()))
+    return cnt_row, cnt_col, best_row, best_col
 
 
 def host_caption_chunks(lens, fractions=(1.0 / 16, 3.0 / 16, 3.0 / 4), multiple=5, min_words=2048):

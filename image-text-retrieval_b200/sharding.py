@@ -53,6 +53,32 @@ class CudaStats:
         return cnt_row, cnt_col, best_row ^ _SIGN, ops.unpack_best_index(best_col)
 
 
+class _BlockShape:
+    """What sharded_ranks needs to know about a score block that is never materialised."""
+
+    def __init__(self, n_img, n_local, device):
+        self.shape, self.device = (n_img, n_local), device
+
+
+class FusedScanStats:
+    """Block statistics straight from the fused SCAN t2i kernel (no score matrix): thresholds = the ground-truth
+    pre-pass on < 1 % of the items, count = the full pass with the comparisons in its epilogue."""
+
+    def __init__(self, pi, pc, raw_feature_norm, agg_func, lambda_softmax, lambda_lse, scores_out=None):
+        self.pi, self.pc, self.args, self.out = pi, pc, (raw_feature_norm, agg_func, lambda_softmax, lambda_lse), scores_out
+
+    def block(self):
+        return _BlockShape(self.pi.n_img, self.pc.n_cap, self.pi.images_bf16.device)
+
+    def thresholds(self, block, cap_offset, caps_per_img):
+        return ops.scan_t2i_gt_thresholds(self.pi, self.pc, *self.args, cap_offset=cap_offset, caps_per_img=caps_per_img)
+
+    def count(self, block, thr_row, thr_col, cap_offset):
+        cnt_row, cnt_col, best_row, best_col = ops.scan_t2i_count(self.pi, self.pc, *self.args, thr_row, thr_col,
+                                                                  cap_offset=cap_offset, out=self.out)
+        return cnt_row, cnt_col, best_row ^ _SIGN, ops.unpack_best_index(best_col)
+
+
 def _world(group):
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group)
@@ -127,9 +153,10 @@ def sharded_scan_eval(images, captions_local, lengths_local, start, n_cap_total,
     grp = group
     if grp is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         grp = dist.group.WORLD
-    block = ev.device_sims(m, images, captions_local, lengths_local, image_group=grp)
-    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in
-                  sharded_ranks(block, start, n_cap_total, group, caps_per_img)]
+    out = ev.fused_ranks(m, images, captions_local, lengths_local, image_group=grp, start=start, n_cap_total=n_cap_total,
+                         caps_per_img=caps_per_img, return_block=return_block)
+    a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in out[:4]]
+    block = out[4] if return_block else None
     res = ev._recall_dict(ev._metrics(a), (a, b), ev._metrics(c), (c, d), verbose=False)
     if return_block:
         res["sims_block"] = block

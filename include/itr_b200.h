@@ -161,6 +161,34 @@ int itr_scan_epilogue_f32(const float* affinity, int n_img, const int32_t* cap_r
                           int cross_attn, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                           float* scores, int64_t ld_scores, void* stream);
 
+/* ---- fused evaluation: scores + i2t / t2i ranking without the score matrix (evaluation.py:124-153 + 156-222) -------
+ * rank of a query = number of scores strictly above its (best) ground-truth score, so the ranks need the ground-truth
+ * scores first:
+ *   1. itr_scan_plan_gt_items (HOST): the (word-tile pair, image tile) items in which a packed caption meets its
+ *      ground-truth image -- global caption cap_offset + c belongs to image (cap_offset + c) / caps_per_img.
+ *   2. itr_scan_t2i_gt_thresholds_bf16: the fused kernel on those items only (< 1 % of the matrix), same packed rows and
+ *      same arithmetic as the full pass, so the thresholds are bit-identical to the scores they are compared with.
+ *      thr_col[c] = score of caption c with its image (NaN if that image is not in [0, n_img)); thr_row[i] = best score
+ *      of image i with its captions AMONG THIS LAUNCH'S (-inf if none).  Multi-GPU: all-reduce(MAX) thr_row across the
+ *      caption shards before step 3.
+ *   3. itr_scan_t2i_count_bf16: the full pass; every score is compared with its thresholds as it is produced:
+ *      cnt_col[c] / cnt_row[i] = #scores strictly above (the t2i rank of caption c / this shard's part of the i2t rank
+ *      of image i), best_col / best_row = max of (orderable(score) << 32 | ~index) (index = image / GLOBAL caption).
+ *      `scores` may be NULL: the matrix is then never written.
+ * Replaces cal_sims + i2t + t2i for SCAN t2i (same feature norms as itr_scan_t2i_scores_bf16). */
+int itr_scan_plan_gt_items(const int32_t* row_meta_host, int n_tiles, int cap_offset, int caps_per_img, int n_img,
+                           int32_t* items_host, int max_items, int* n_items);
+int itr_scan_t2i_gt_thresholds_bf16(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                                    const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                                    int n_tiles, int n_cap, const int32_t* items, int n_items, int feature_norm, int agg,
+                                    float lambda_softmax, float lambda_lse, int cap_offset, int caps_per_img,
+                                    float* thr_col, float* thr_row, void* stream);
+int itr_scan_t2i_count_bf16(const uint16_t* images_bf16, const void* gram_pack, int n_img,
+                            const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
+                            int n_tiles, int n_cap, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
+                            int cap_offset, const float* thr_col, const float* thr_row, float* scores, int64_t ld_scores,
+                            int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col, void* stream);
+
 /* Debug / bring-up: raw region-word affinities of ONE (word tile, image tile) pair as the
  * tensor cores produced them: out[128 rows][144 cols] fp32. */
 int itr_scan_t2i_affinity_debug(const uint16_t* images_bf16, int n_img, const uint16_t* words_bf16, int n_tiles,

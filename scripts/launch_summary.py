@@ -30,5 +30,5 @@ for n, s in enumerate(starts):
     kind = "end-to-end step (captions gathered from pinned host memory by pack_words_kernel)" if pack > 5.0 else "device-resident step"
     print("\nstep {}: {}  ({} launches, {:.3f} ms of kernel time)".format(n, kind, len(step), tot))
     for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        ours = "(ours)" if ("itr::" in k or "tc::" in k) else "(torch plumbing)"
+        ours = "(ours)" if ("itr::" in k or "tc::" in k or "tc2::" in k) else "(torch plumbing)"
         print("  {:86s} x{:<3d} {:10.3f} ms {:6.2f}% {}".format(k[:86], c, v, 100 * v / tot, ours))

@@ -241,3 +241,91 @@ def test_tc_pipelined_host_captions_match_device_path():
         got = ops.scan_t2i_scores_from_host(pi, host, ln, "clipped_l2norm", "LogSumExp", 9.0, 6.0, chunks=ch)
         torch.cuda.synchronize()
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused evaluation: ranking inside the score kernel (ground-truth pre-pass + counting epilogue), no score matrix
+def _fused_vs_matrix(n_img, n_cap, lam, seed, lengths=None, agg="LogSumExp", shards=1):
+    img, cap, lens = itr_b200.synth.scan_inputs(n_img, n_cap, lam, seed, device="cuda", lengths=lengths)
+    pi = ops.prepare_images(img)
+    args = ("clipped_l2norm", agg, 9.0, 6.0)
+    pc_all = ops.prepare_captions(cap, lens)
+    scores = ops.scan_t2i_scores_bf16(pi, pc_all, *args)
+    want = [x.cpu().numpy() for x in ev.device_ranks(scores)]
+    # per shard: thresholds from the pre-pass, merged like the multi-GPU exchange (max of thresholds, sum of counts,
+    # max of keys), then the counting pass
+    bounds = sharding.shard_bounds(n_cap, shards)
+    pcs = [ops.prepare_captions(cap[lo:hi], lens[lo:hi]) if hi > lo else None for lo, hi in bounds]
+    thr_row = torch.full((n_img,), float("-inf"), device="cuda")
+    thr_cols = []
+    for (lo, hi), pc in zip(bounds, pcs):
+        if pc is None:
+            thr_cols.append(None)
+            continue
+        tr, tc_ = ops.scan_t2i_gt_thresholds(pi, pc, *args, cap_offset=lo, caps_per_img=5)
+        thr_row = torch.maximum(thr_row, tr)
+        thr_cols.append(tc_)
+        # the thresholds ARE the matrix entries, bit for bit
+        gt_img = (torch.arange(lo, hi, device="cuda") // 5)
+        has = gt_img < n_img
+        assert torch.equal(tc_[has], scores[gt_img[has], torch.arange(lo, hi, device="cuda")[has]])
+        assert torch.isnan(tc_[~has]).all()
+    i2t = torch.zeros(n_img, dtype=torch.int64, device="cuda")
+    best = torch.zeros(n_img, dtype=torch.int64, device="cuda")
+    t2i, t2i_top = [], []
+    for (lo, hi), pc, tc_ in zip(bounds, pcs, thr_cols):
+        if pc is None:
+            continue
+        out = torch.full((n_img, hi - lo), float("nan"), device="cuda")
+        cr, cc, br, bc = ops.scan_t2i_count(pi, pc, *args, thr_row, tc_, cap_offset=lo, out=out)
+        assert torch.equal(out, scores[:, lo:hi])                       # the optional matrix is the same matrix
+        cr2, cc2, br2, bc2 = ops.scan_t2i_count(pi, pc, *args, thr_row, tc_, cap_offset=lo)      # and without it
+        assert torch.equal(cr, cr2) and torch.equal(cc, cc2) and torch.equal(br, br2) and torch.equal(bc, bc2)
+        i2t += cr.long()
+        best = torch.maximum(best ^ sharding._SIGN, br ^ sharding._SIGN) ^ sharding._SIGN
+        t2i.append(cc.long()); t2i_top.append(ops.unpack_best_index(bc))
+    np.testing.assert_array_equal(i2t.cpu().numpy(), want[0])
+    np.testing.assert_array_equal(torch.cat(t2i).cpu().numpy(), want[2])
+    np.testing.assert_array_equal(ops.unpack_best_index(best).cpu().numpy(), want[1])
+    has_gt = (np.arange(n_cap) // 5) < n_img                             # top-1 of a caption without an image is undefined
+    np.testing.assert_array_equal(torch.cat(t2i_top).cpu().numpy()[has_gt], want[3][has_gt])
+
+
+@pytest.mark.parametrize("n_img,n_cap,shards", [(10, 50, 1), (37, 185, 1), (37, 185, 3), (64, 333, 2), (5, 25, 4), (130, 650, 1)])
+def test_fused_ranking_matches_matrix_ranking(n_img, n_cap, shards):
+    _fused_vs_matrix(n_img, n_cap, 10.5, 31 + n_img, shards=shards)
+
+
+def test_fused_ranking_long_captions_and_other_aggregations():
+    lens = np.array([72, 40, 33, 128, 3, 5, 17, 32, 31, 1] * 4, dtype=np.int32)
+    for agg in ("LogSumExp", "Mean", "Max", "Sum"):
+        _fused_vs_matrix(8, 40, 10.5, 77, lengths=lens, agg=agg, shards=2)
+
+
+def test_cal_sims_and_recall_never_builds_the_matrix():
+    """cal_sims_and_recall(return_sims=False) on the tensor-core SCAN t2i path: same dict as the matrix path, and no
+    (n_img, n_cap) allocation: its peak device memory is lower than the matrix path's by the size of the matrix."""
+    n_img, n_cap = 1000, 5000
+    img, cap, lens = itr_b200.synth.scan_inputs(n_img, n_cap, 10.5, 8, device="cuda")
+    model = FakeModel(cfg())
+
+    def peak_of(**kw):
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        res = ev.cal_sims_and_recall(model, img, cap, lens, **kw)
+        torch.cuda.synchronize()
+        return res, torch.cuda.max_memory_allocated() - base
+
+    peak_of()                                   # warm the plan caches so both measured runs allocate the same operands
+    got, peak_fused = peak_of()
+    want, peak_matrix = peak_of(return_sims=True)
+    assert want.pop("sims").shape == (n_img, n_cap)
+    for k in want:
+        if isinstance(want[k], np.ndarray):
+            np.testing.assert_array_equal(got[k], want[k])
+        else:
+            assert got[k] == want[k], k
+    matrix_bytes = n_img * n_cap * 4
+    assert peak_matrix - peak_fused >= 0.9 * matrix_bytes, (peak_matrix, peak_fused, matrix_bytes)
