@@ -112,23 +112,22 @@ extern "C" int itr_scan_plan_words(const int32_t* cap_lens_host, int n_cap, int3
   return ITR_OK;
 }
 
-// Items of the ground-truth pre-pass of the fused evaluation (itr_scan_t2i_gt_thresholds_bf16): every
-// (word-tile PAIR, image tile) combination in which some packed caption meets its ground-truth image
-// (global caption cap_offset + c belongs to image (cap_offset + c) / caps_per_img; images come in tiles of
-// ITR_TILE_IMAGES).  items_host receives (pair, image tile) int32 couples sorted by image tile, or may be NULL to
-// just count them; returns the count through *n_items.
+// Items of the ground-truth pre-pass of the fused evaluation (itr_scan_t2i_gt_thresholds_bf16).  A word tile "needs"
+// an image tile when one of its packed captions belongs to one of the tile's images (global caption cap_offset + c
+// belongs to image (cap_offset + c) / caps_per_img; images come in tiles of ITR_TILE_IMAGES).  The CTA pair of the kernel
+// scores TWO word tiles against one image tile per item, so the word tiles that need image tile n are paired up:
+// items_host receives int32 quadruples (word tile of the leader, word tile of the peer or n_tiles for none, image
+// tile, 0), sorted by image tile, or may be NULL to just count them; returns the count through *n_items.
 extern "C" int itr_scan_plan_gt_items(const int32_t* row_meta_host, int n_tiles, int cap_offset, int caps_per_img, int n_img,
                                       int32_t* items_host, int max_items, int* n_items) {
   if (!row_meta_host || !n_items || n_tiles < 0 || cap_offset < 0 || caps_per_img < 1 || n_img < 0)
     return itr::fail(ITR_ERR_INVALID, "itr_scan_plan_gt_items: bad arguments");
-  const int n_pairs = (n_tiles + 1) / 2;
   const int n_it = (n_img + ITR_TILE_IMAGES - 1) / ITR_TILE_IMAGES;
-  std::vector<std::pair<int, int>> items;      // (image tile, pair)
+  std::vector<std::pair<int, int>> needs;      // (image tile, word tile)
   std::vector<int> seen;
-  for (int mp = 0; mp < n_pairs; ++mp) {
+  for (int t = 0; t < n_tiles; ++t) {
     seen.clear();
-    const int row_end = std::min(n_tiles, 2 * mp + 2) * ITR_TILE_WORDS;
-    for (int row = 2 * mp * ITR_TILE_WORDS; row < row_end; ++row) {
+    for (int row = t * ITR_TILE_WORDS; row < (t + 1) * ITR_TILE_WORDS; ++row) {
       const int32_t* m = row_meta_host + 4 * (size_t)row;
       if (m[0] < 0 || m[1] != 0) continue;      // one look per caption: its first word
       const long long img = ((long long)cap_offset + m[0]) / caps_per_img;
@@ -137,13 +136,20 @@ extern "C" int itr_scan_plan_gt_items(const int32_t* row_meta_host, int n_tiles,
     }
     std::sort(seen.begin(), seen.end());
     seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
-    for (int n : seen) if (n < n_it) items.emplace_back(n, mp);
+    for (int n : seen) if (n < n_it) needs.emplace_back(n, t);
   }
-  std::sort(items.begin(), items.end());
-  *n_items = (int)items.size();
-  if (items_host) {
-    if ((int)items.size() > max_items) return itr::fail(ITR_ERR_INVALID, "itr_scan_plan_gt_items: %d items do not fit in %d", (int)items.size(), max_items);
-    for (size_t i = 0; i < items.size(); ++i) { items_host[2 * i] = items[i].second; items_host[2 * i + 1] = items[i].first; }
+  std::sort(needs.begin(), needs.end());
+  int count = 0;
+  for (size_t i = 0; i < needs.size();) {
+    const bool partner = i + 1 < needs.size() && needs[i + 1].first == needs[i].first;
+    if (items_host) {
+      if (count >= max_items) return itr::fail(ITR_ERR_INVALID, "itr_scan_plan_gt_items: more than %d items", max_items);
+      int32_t* e = items_host + 4 * (size_t)count;
+      e[0] = needs[i].second; e[1] = partner ? needs[i + 1].second : n_tiles; e[2] = needs[i].first; e[3] = 0;
+    }
+    ++count;
+    i += partner ? 2 : 1;
   }
+  *n_items = count;
   return ITR_OK;
 }

@@ -148,13 +148,14 @@ __device__ __forceinline__ void sts_f2(uint32_t addr, float x, float y) {
 // Work unit = (band of BAND consecutive word-tile PAIRS, image tile n); a CTA pair takes units u = pair, pair + #pairs, ...
 // and walks the band against the SAME image tile (see scan_t2i_tc.cu: an image tile comes from HBM once per band,
 // the band stays L2-resident).
-// With an explicit item list (the ground-truth pre-pass of the fused evaluation) a unit is one listed
-// (word-tile pair, image tile) item.
+// With an explicit item list (the ground-truth pre-pass of the fused evaluation) a unit is one listed item
+// (word tile of the leader, word tile of the peer, image tile): the two CTAs take ANY two word tiles that need that
+// image tile (a tile index >= n_wt means "none").
 template <bool LIST>
 struct ScheduleT {
   int n_wp, n_it, n_bands, last_band;
-  const int2* items; int n_items;
-  __device__ ScheduleT(int n_wp_, int n_it_, const int2* items_, int n_items_) : n_wp(n_wp_), n_it(n_it_), items(items_), n_items(n_items_) {
+  const int4* items; int n_items;
+  __device__ ScheduleT(int n_wp_, int n_it_, const int4* items_, int n_items_) : n_wp(n_wp_), n_it(n_it_), items(items_), n_items(n_items_) {
     n_bands = (n_wp + BAND - 1) / BAND;
     last_band = n_wp - (n_bands - 1) * BAND;
   }
@@ -163,11 +164,14 @@ struct ScheduleT {
 template <bool LIST>
 struct ItemIterT {
   const ScheduleT<LIST>& s;
-  int u, step, m, n, left;      // m = word-tile PAIR index
+  int u, step, m, n, left;      // m = word-tile PAIR index (LIST: the leader's word tile)
+  int m_peer;                   // LIST: the peer's word tile
+  // word tile of CTA `rank` of the pair
+  __device__ int tile(int rank) const { return LIST ? (rank ? m_peer : m) : 2 * m + rank; }
   __device__ ItemIterT(const ScheduleT<LIST>& s_, int first, int step_) : s(s_), u(first), step(step_) { open(); }
   __device__ void open() {
     if (LIST) {
-      if (u < s.n_items) { const int2 e = s.items[u]; m = e.x; n = e.y; left = 1; }
+      if (u < s.n_items) { const int4 e = s.items[u]; m = e.x; m_peer = e.y; n = e.z; left = 1; }
       return;
     }
     if (u < s.units()) {
@@ -195,7 +199,7 @@ struct Params {
   long long* prof;             // optional [cluster][2][16] cycle counters (PROF instantiation)
   // fused evaluation (i2t / t2i ranking, evaluation.py:156-222): caption c of this launch is global caption cap_offset + c,
   // whose ground-truth image is (cap_offset + c) / cpi
-  const int2* items; int n_items;          // MODE_GT: the (word-tile pair, image tile) items that hold a ground-truth pair
+  const int4* items; int n_items;          // MODE_GT: (leader's word tile, peer's word tile, image tile, 0) items that hold ground-truth pairs
   int cap_offset, cpi;
   float* thr_col;                          // [n_cap]  MODE_GT: written; MODE_COUNT: read (NaN = no ground-truth image here)
   unsigned int* thr_row_key;               // [n_img]  MODE_GT: atomicMax of the orderable key of the ground-truth scores
@@ -217,6 +221,7 @@ __device__ __forceinline__ float seg_total(float x, const bool (&p)[5], int seg_
 
 struct Carry {
   float P, D, wnorm;
+  float thr_c, thr_r;          // MODE_COUNT: thresholds of the row's caption / the group's image, fetched an item ahead
   int cap, seg, n_words, img, b;
   bool valid, img_ok, live;
 };
@@ -285,7 +290,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     int stage = 0; uint32_t phase = 0;
     long long w_empty = 0; const long long t_begin = prof_on ? clock64() : 0;
     for (ItemIter item(sched, first, step); item.valid(); item.next()) {
-      const int row_w = (2 * item.m + (int)rank) * BLOCK_M;            // rows past the tensor are zero-filled
+      const int row_w = item.tile((int)rank) * BLOCK_M;                // rows past the tensor are zero-filled
       const int row_i = item.n * BLOCK_N + (int)rank * HALF_N;
 #pragma unroll 1
       for (int kb = 0; kb < K_BLOCKS; ++kb) {
@@ -376,7 +381,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     // =============================== aux loader (both CTAs) ================================
     int it = 0;
     for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
-      const int m = 2 * item.m + (int)rank, n = item.n;
+      const int m = item.tile((int)rank), n = item.n;
       const int b = it & 1;
       mbar_wait_sleep(aempty_bar(b), ((it >> 1) & 1) ^ 1);
       if (elect_one()) {
@@ -411,7 +416,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     uint32_t hvp[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k) hvp[k] = 0u;
-    c.live = false; c.valid = false; c.img_ok = false; c.P = c.D = c.wnorm = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
+    c.live = false; c.valid = false; c.img_ok = false; c.P = c.D = c.wnorm = 0.f; c.thr_c = c.thr_r = 0.f; c.cap = -1; c.seg = 0; c.n_words = 0; c.img = 0; c.b = 0;
 
     auto phase_b = [&]() {
       if (c.img_ok) {
@@ -472,7 +477,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
             if (p.scores) p.scores[(size_t)c.img * p.ld + c.cap] = tot;
             // rank = #scores strictly above the ground-truth score; a score can be the arg-max of its row / column only
             // if it is not below that score, so the packed keys are built on the rare path only
-            const float tc = p.thr_col[c.cap], tr = p.thr_row[c.img];
+            const float tc = c.thr_c, tr = c.thr_r;
             if (!(tot < tc)) {
               if (tot > tc) atomicAdd(p.cnt_col + c.cap, 1);
               atomicMax(p.best_col + c.cap, ((unsigned long long)orderable(tot) << 32) | (unsigned)(~(unsigned)c.img));
@@ -494,7 +499,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     int it = 0;
     for (ItemIter item(sched, first, step); item.valid(); item.next(), ++it) {
       const int n = item.n;
-      const int m = 2 * item.m + (int)rank;
+      const int m = item.tile((int)rank);
       const bool word_ok = m < p.n_wt;
       const int b = it & 1;
       mbar_wait_sleep_t(afull_bar(b), (it >> 1) & 1, w_afull, prof_on);
@@ -510,6 +515,10 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       const int img = n * IMGS + g;
       const bool img_ok = img < p.n_img;
       const bool valid = img_ok && word_ok;
+      // MODE_COUNT: the two thresholds this row's score will be compared with, requested now and consumed in phase B one
+      // item later (a dependent global load inside phase B costs every warp an L2 round trip per item)
+      float thr_c = 0.f, thr_r = 0.f;
+      if (MODE == MODE_COUNT && valid && meta.x >= 0) { thr_c = p.thr_col[meta.x]; thr_r = p.thr_row[img]; }
 
       const uint32_t tacc = tmem_base + b * ACC_PITCH + lane_sel;
       mbar_wait_sleep_t(tfull_bar(b), (it >> 1) & 1, w_tfull, prof_on);
@@ -635,6 +644,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
 #pragma unroll
       for (int k = 0; k < 18; ++k) hvp[k] = hv[k];
       c.P = P; c.D = Dd; c.wnorm = wnorm; c.cap = meta.x; c.seg = meta.z; c.n_words = meta.w;
+      if (MODE == MODE_COUNT) { c.thr_c = thr_c; c.thr_r = thr_r; }
       c.img = img; c.b = b; c.valid = valid; c.img_ok = img_ok; c.live = true;
     }
     phase_b();
@@ -771,7 +781,7 @@ int launch_tc2_gt(const uint16_t* images_bf16, const void* gram_pack, int n_img,
                        lambda_softmax, lambda_lse);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
-  p.items = reinterpret_cast<const int2*>(items); p.n_items = n_items;
+  p.items = reinterpret_cast<const int4*>(items); p.n_items = n_items;
   p.cap_offset = cap_offset; p.cpi = cpi;
   p.thr_col = thr_col;
   p.thr_row_key = reinterpret_cast<unsigned int*>(thr_row);        // keys first, converted in place below

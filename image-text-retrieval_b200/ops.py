@@ -299,8 +299,8 @@ _GT_ITEMS_CACHE = {}
 
 
 def gt_items(pc: "PreparedCaptions", cap_offset, caps_per_img, n_img):
-    """(items int32 (n_items, 2) on the device, n_items): the (word-tile pair, image tile) items of the ground-truth
-    pre-pass for this packing (csrc/plan.cpp, itr_scan_plan_gt_items), memoised next to the plan."""
+    """(items int32 (n_items, 4) on the device, n_items): the (leader's word tile, peer's word tile, image tile, 0) items
+    of the ground-truth pre-pass for this packing (csrc/plan.cpp, itr_scan_plan_gt_items), memoised next to the plan."""
     key = (pc.plan_key, int(cap_offset), int(caps_per_img), int(n_img), str(pc.row_meta.device))
     hit = _GT_ITEMS_CACHE.pop(key, None) if pc.plan_key is not None else None
     if hit is None:
@@ -310,7 +310,7 @@ def gt_items(pc: "PreparedCaptions", cap_offset, caps_per_img, n_img):
         n = capi.C.c_int(0)
         check(L.itr_scan_plan_gt_items(meta.ctypes.data, pc.n_tiles, int(cap_offset), int(caps_per_img), int(n_img), None, 0,
                                        capi.C.byref(n)))
-        items = np.empty((max(n.value, 1), 2), dtype=np.int32)
+        items = np.empty((max(n.value, 1), 4), dtype=np.int32)
         check(L.itr_scan_plan_gt_items(meta.ctypes.data, pc.n_tiles, int(cap_offset), int(caps_per_img), int(n_img),
                                        items.ctypes.data, n.value, capi.C.byref(n)))
         hit = (torch.from_numpy(items).to(pc.row_meta.device), n.value)

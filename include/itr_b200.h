@@ -164,8 +164,9 @@ int itr_scan_epilogue_f32(const float* affinity, int n_img, const int32_t* cap_r
 /* ---- fused evaluation: scores + i2t / t2i ranking without the score matrix (evaluation.py:124-153 + 156-222) -------
  * rank of a query = number of scores strictly above its (best) ground-truth score, so the ranks need the ground-truth
  * scores first:
- *   1. itr_scan_plan_gt_items (HOST): the (word-tile pair, image tile) items in which a packed caption meets its
- *      ground-truth image -- global caption cap_offset + c belongs to image (cap_offset + c) / caps_per_img.
+ *   1. itr_scan_plan_gt_items (HOST): int32 quadruples (word tile A, word tile B or n_tiles, image tile, 0): two word
+ *      tiles in which a packed caption meets a ground-truth image of that image tile -- global caption cap_offset + c
+ *      belongs to image (cap_offset + c) / caps_per_img.
  *   2. itr_scan_t2i_gt_thresholds_bf16: the fused kernel on those items only (< 1 % of the matrix), same packed rows and
  *      same arithmetic as the full pass, so the thresholds are bit-identical to the scores they are compared with.
  *      thr_col[c] = score of caption c with its image (NaN if that image is not in [0, n_img)); thr_row[i] = best score

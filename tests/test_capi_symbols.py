@@ -107,3 +107,34 @@ def test_plan_words_fuzz():
         check_plan(lens)
 
     run()
+
+
+def test_gt_item_planner_covers_every_ground_truth_pair():
+    """itr_scan_plan_gt_items: every caption's word tile appears in an item with the image tile of its ground-truth
+    image; word tiles are paired per image tile (never two items for the same (tile, image tile)); shards use the
+    global caption index."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    L = capi.lib()
+    for n_cap, n_img, cap_offset in [(0, 4, 0), (5, 1, 0), (333, 64, 0), (640, 130, 0), (200, 130, 450), (77, 9, 0)]:
+        lens = rng.integers(1, 40, size=n_cap).astype(np.int32)
+        if n_cap:
+            lens[rng.integers(0, n_cap)] = 128
+        meta, n_tiles = ops.plan_words(lens) if n_cap else (np.zeros((0, 4), np.int32), 0)
+        n = C.c_int(-1)
+        buf = np.ascontiguousarray(meta if n_tiles else np.zeros((1, 4), np.int32))
+        capi.check(L.itr_scan_plan_gt_items(buf.ctypes.data, n_tiles, cap_offset, 5, n_img, None, 0, C.byref(n)))
+        items = np.empty((max(n.value, 1), 4), dtype=np.int32)
+        capi.check(L.itr_scan_plan_gt_items(buf.ctypes.data, n_tiles, cap_offset, 5, n_img, items.ctypes.data, n.value, C.byref(n)))
+        items = items[: n.value]
+        m = meta.reshape(-1, 4)
+        rows = np.nonzero((m[:, 0] >= 0) & (m[:, 1] == 0))[0]
+        img = (cap_offset + m[rows, 0]) // 5
+        need = {(int(r // 128), int(i // 4)) for r, i in zip(rows, img) if i < n_img}
+        have = [(int(a), int(t)) for a, b, t, z in items] + [(int(b), int(t)) for a, b, t, z in items if b < n_tiles]
+        assert len(have) == len(set(have)) and set(have) == need
+        assert (items[:, 3] == 0).all() and (items[:, 0] < max(n_tiles, 1)).all() and (items[:, 1] <= n_tiles).all()
+        assert (np.diff(items[:, 2]) >= 0).all()                                # sorted by image tile
+        if n.value > 1:
+            with pytest.raises(ValueError):
+                capi.check(L.itr_scan_plan_gt_items(buf.ctypes.data, n_tiles, cap_offset, 5, n_img, items.ctypes.data, n.value - 1, C.byref(n)))
