@@ -428,10 +428,10 @@ def main():
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(seg_ms, op=dist.ReduceOp.MAX)
     if args.rank_mode == "matrix":
-        names = ["prep_images" + ("+all_gather" if world > 1 else ""), "pack_captions", "score_kernel",
+        names = ["prep_images" + ("(+async gather)" if world > 1 else ""), "pack_captions", "score_kernel",
                  "rank_kernels" + ("+exchange" if world > 1 else "")]
     else:
-        names = ["prep_images" + ("+all_gather" if world > 1 else ""), "pack_captions", "host_setup",
+        names = ["prep_images" + ("(+async gather)" if world > 1 else ""), "pack_captions", "host_setup",
                  "gt_prepass+score_count_kernel" + ("+exchange" if world > 1 else "")]
     breakdown = dict(zip(names, [round(x, 3) for x in seg_ms.tolist()]))
     breakdown["score_kernel_alone"] = round(kern_ms.item(), 3)
@@ -540,7 +540,8 @@ def main():
                    "l2_policy": "inputs larger than L2 (bf16 operands {:.0f} MB per GPU{})".format(
                        (n_img * R * D * 2 + n_tiles * 128 * D * 2) / 1e6,
                        "" if args.rank_mode == "fused" else " + {:.0f} MB score block".format(n_img * (hi - lo) * 4 / 1e6)),
-                   "step": "prep(cast,pack,gram" + (", image shards all-gathered over NCCL" if world > 1 else "") + ") + " +
+                   "step": "prep(cast,pack,gram" + (", image shards pulled from the peers' symmetric memory by the copy engines while the local shard is scored"
+                                                         if world > 1 else "") + ") + " +
                            ("ground-truth pre-pass + tcgen05 scores with the ranking in the epilogue (no score matrix)" if args.rank_mode == "fused"
                             else "tcgen05 scores + rank kernels") + (" + rank exchange" if world > 1 else "")},
         "eval_wall_ms": {"device": ms_per_step, "e2e": e2e_s.item() * 1e3},

@@ -201,6 +201,7 @@ struct Params {
   // whose ground-truth image is (cap_offset + c) / cpi
   const int4* items; int n_items;          // MODE_GT: (leader's word tile, peer's word tile, image tile, 0) items that hold ground-truth pairs
   int cap_offset, cpi;
+  int img_offset;                          // MODE_COUNT: global index of image 0 of this launch (arg-max keys of the columns)
   float* thr_col;                          // [n_cap]  MODE_GT: written; MODE_COUNT: read (NaN = no ground-truth image here)
   unsigned int* thr_row_key;               // [n_img]  MODE_GT: atomicMax of the orderable key of the ground-truth scores
   const float* thr_row;                    // [n_img]  MODE_COUNT
@@ -480,7 +481,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
             const float tc = c.thr_c, tr = c.thr_r;
             if (!(tot < tc)) {
               if (tot > tc) atomicAdd(p.cnt_col + c.cap, 1);
-              atomicMax(p.best_col + c.cap, ((unsigned long long)orderable(tot) << 32) | (unsigned)(~(unsigned)c.img));
+              atomicMax(p.best_col + c.cap, ((unsigned long long)orderable(tot) << 32) | (unsigned)(~(unsigned)(p.img_offset + c.img)));
             }
             if (!(tot < tr)) {
               if (tot > tr) atomicAdd(p.cnt_row + c.img, 1);
@@ -800,7 +801,7 @@ int launch_tc2_count(const uint16_t* images_bf16, const void* gram_pack, int n_i
                      const int32_t* row_meta, const float* row_wnorm, int n_tiles, int n_cap, int feature_norm, int agg,
                      float lambda_softmax, float lambda_lse, int cap_offset, const float* thr_col, const float* thr_row,
                      float* scores, int64_t ld_scores, int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col,
-                     void* stream) {
+                     int img_offset, int accumulate, void* stream) {
   CUtensorMap map_w, map_i;
   Params p{};
   int rc = fill_params(p, map_w, map_i, images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, feature_norm, agg,
@@ -808,14 +809,16 @@ int launch_tc2_count(const uint16_t* images_bf16, const void* gram_pack, int n_i
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   p.scores = scores; p.ld = ld_scores;
-  p.cap_offset = cap_offset; p.cpi = 1;
+  p.cap_offset = cap_offset; p.cpi = 1; p.img_offset = img_offset;
   p.thr_col = const_cast<float*>(thr_col); p.thr_row = thr_row;
   p.cnt_row = cnt_row; p.cnt_col = cnt_col;
   p.best_row = reinterpret_cast<unsigned long long*>(best_row); p.best_col = reinterpret_cast<unsigned long long*>(best_col);
-  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_row, 0, sizeof(int32_t) * (size_t)n_img, st));
-  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, sizeof(int32_t) * (size_t)n_cap, st));
+  ITR_CHECK_CUDA(cudaMemsetAsync(cnt_row, 0, sizeof(int32_t) * (size_t)n_img, st));        // rows belong to this launch alone
   ITR_CHECK_CUDA(cudaMemsetAsync(best_row, 0, sizeof(uint64_t) * (size_t)n_img, st));
-  ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, sizeof(uint64_t) * (size_t)n_cap, st));
+  if (!accumulate) {                                                                         // columns may collect several image ranges
+    ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, sizeof(int32_t) * (size_t)n_cap, st));
+    ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, sizeof(uint64_t) * (size_t)n_cap, st));
+  }
   return p.clipped ? launch<false, true, MODE_COUNT>(map_w, map_i, p, st) : launch<false, false, MODE_COUNT>(map_w, map_i, p, st);
 }
 
@@ -871,8 +874,10 @@ extern "C" int itr_scan_t2i_count_bf16(const uint16_t* images_bf16, const void* 
                                        const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                                        int n_tiles, int n_cap, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                                        int cap_offset, const float* thr_col, const float* thr_row, float* scores, int64_t ld_scores,
-                                       int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col, void* stream) {
+                                       int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col,
+                                       int img_offset, int accumulate_columns, void* stream) {
   ITR_TC2_COMMON_CHECKS("itr_scan_t2i_count_bf16");
+  ITR_REQUIRE(img_offset >= 0, "itr_scan_t2i_count_bf16: img_offset < 0");
   ITR_REQUIRE(thr_col && thr_row && cnt_row && cnt_col && best_row && best_col, "itr_scan_t2i_count_bf16: null pointer");
   ITR_REQUIRE(!scores || ld_scores >= n_cap, "itr_scan_t2i_count_bf16: ld_scores < n_cap");
   if (n_img == 0 && n_cap == 0) return ITR_OK;
@@ -881,10 +886,10 @@ extern "C" int itr_scan_t2i_count_bf16(const uint16_t* images_bf16, const void* 
   if (n_img == 0 || n_tiles == 0 || n_cap == 0) {
     cudaStream_t st = as_stream(stream);
     if (n_img) { ITR_CHECK_CUDA(cudaMemsetAsync(cnt_row, 0, 4 * (size_t)n_img, st)); ITR_CHECK_CUDA(cudaMemsetAsync(best_row, 0, 8 * (size_t)n_img, st)); }
-    if (n_cap) { ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, 4 * (size_t)n_cap, st)); ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, 8 * (size_t)n_cap, st)); }
+    if (n_cap && !accumulate_columns) { ITR_CHECK_CUDA(cudaMemsetAsync(cnt_col, 0, 4 * (size_t)n_cap, st)); ITR_CHECK_CUDA(cudaMemsetAsync(best_col, 0, 8 * (size_t)n_cap, st)); }
     return ITR_OK;
   }
   return tc2::launch_tc2_count(images_bf16, gram_pack, n_img, words_bf16, row_meta, row_wnorm, n_tiles, n_cap, feature_norm, agg,
                                lambda_softmax, lambda_lse, cap_offset, thr_col, thr_row, scores, ld_scores, cnt_row, cnt_col,
-                               best_row, best_col, stream);
+                               best_row, best_col, img_offset, accumulate_columns, stream);
 }

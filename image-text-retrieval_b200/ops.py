@@ -248,6 +248,29 @@ class PreparedImages:
     images_bf16: torch.Tensor     # (n_img, 36, 1024) bf16
     gram_pack: torch.Tensor       # (n_img, 4752) u8: fp16 off-diagonal Gram (UMMA layout) + fp32 diagonal
     n_img: int
+    # multi-GPU (prepare_images_sharded): the rows this rank prepared itself are valid at once; the other ranks' rows
+    # are being pulled over NVLink by the copy engines and are valid once `gathered` has been waited for
+    local_rows: tuple = None
+    gathered: object = None       # torch.cuda.Event recorded on the gather stream
+
+    def rows(self, lo, hi):
+        """The images [lo, hi) as a PreparedImages of their own (views)."""
+        return PreparedImages(self.images_bf16[lo:hi], self.gram_pack[lo:hi], hi - lo)
+
+    def wait_gathered(self):
+        """Make the current stream wait until every rank's rows have arrived (no-op on one GPU)."""
+        if self.gathered is not None:
+            torch.cuda.current_stream(self.images_bf16.device).wait_event(self.gathered)
+            self.gathered = None
+
+    def row_ranges(self):
+        """[(lo, hi, needs_gather)] in the order the rows become valid: this rank's own rows first."""
+        if self.gathered is None or self.local_rows is None:
+            return [(0, self.n_img, self.gathered is not None)]
+        lo, hi = self.local_rows
+        out = [(lo, hi, False)] if hi > lo else []
+        out += [(a, b, True) for a, b in ((0, lo), (hi, self.n_img)) if b > a]
+        return out
 
 
 @dataclass
@@ -335,20 +358,71 @@ def plan_words(lengths: np.ndarray):
     return meta[: n_tiles * capi.TILE_WORDS], n_tiles
 
 
-def prepare_images(images) -> PreparedImages:
+def prepare_images(images, out=None, gram=None) -> PreparedImages:
     images = _cuda_f32(images, "images")
     n_img = images.size(0)
-    out = torch.empty(n_img, capi.REGIONS, capi.EMBED, device=images.device, dtype=torch.bfloat16)
-    gram = torch.empty(n_img, capi.GRAM_BYTES, device=images.device, dtype=torch.uint8)
+    if out is None:
+        out = torch.empty(n_img, capi.REGIONS, capi.EMBED, device=images.device, dtype=torch.bfloat16)
+    if gram is None:
+        gram = torch.empty(n_img, capi.GRAM_BYTES, device=images.device, dtype=torch.uint8)
+    assert out.is_contiguous() and gram.is_contiguous() and out.shape[0] == n_img and gram.shape[0] == n_img
     with torch.cuda.device(images.device):
         check(capi.lib().itr_scan_prep_images_bf16(ptr(images), n_img, images.size(1), images.size(2), ptr(out), ptr(gram),
                                                    stream_ptr()))
     return PreparedImages(out, gram, n_img)
 
 
+_SYM = {}              # (group name, device) -> symmetric-memory workspace of the image gather
+_GATHER_STREAMS = {}
+
+
+def _gather_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _GATHER_STREAMS:
+        _GATHER_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _GATHER_STREAMS[key]
+
+
+def _sym_workspace(group, nbytes, dev):
+    """A symmetric-memory buffer of >= nbytes on every rank of `group` (torch.distributed._symmetric_memory): each rank
+    can map its peers' buffers and pull from them with plain device-to-device copies, which run on the copy engines
+    over NVLink and leave every SM to the score kernel.  None when symmetric memory is unavailable (-> NCCL)."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("ITR_B200_GATHER", "").lower() == "nccl":
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        if dist.get_backend(pg) != "nccl":
+            return None
+        name = pg.group_name
+        key = (name, str(dev))
+        ent = _SYM.get(key)
+        if ent is None or ent["nbytes"] < nbytes:
+            size = max(nbytes, 1 << 20)
+            buf = symm.empty(size, dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(buf, name)
+            ent = {"buf": buf, "hdl": hdl, "nbytes": size, "done": None}
+            _SYM[key] = ent
+        return ent
+    except Exception as exc:      # noqa: BLE001  (no fabric / IPC support on this box: fall back to the NCCL all-gather)
+        _SYM[("failed", str(dev))] = repr(exc)
+        os.environ["ITR_B200_GATHER"] = "nccl"
+        return None
+
+
+def image_shard_bounds(n_img, world):
+    per = (n_img + world - 1) // world
+    return per, [(min(r * per, n_img), min((r + 1) * per, n_img)) for r in range(world)]
+
+
 def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
     """Multi-GPU form of prepare_images: every rank casts / Grams only its slice of the images (and, for host
-    input, uploads only that slice), then the bf16 regions and Gram packs are all-gathered over NVLink.
+    input, uploads only that slice); the other slices are then PULLED from the peers' symmetric-memory buffers by the
+    copy engines on a side stream (no SMs, no NCCL kernel), so the caller can score its own slice meanwhile:
+    the result's `local_rows` are valid at once, the rest after `wait_gathered()` (every consumer in this module
+    waits by itself).  Without symmetric memory the slices are all-gathered with NCCL before returning.
     `images` is the FULL (n_img, 36, 1024) array on every rank: a host numpy array / tensor or a CUDA tensor."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -360,8 +434,8 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
         return prepare_images(t.to(d_, non_blocking=True))
     rank = dist.get_rank(group)
     n_img = len(images)
-    per = (n_img + world - 1) // world
-    lo, hi = min(rank * per, n_img), min((rank + 1) * per, n_img)
+    per, bounds = image_shard_bounds(n_img, world)
+    lo, hi = bounds[rank]
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     sl = images[lo:hi]
     if not isinstance(sl, torch.Tensor):
@@ -374,16 +448,48 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
         sl = sl.to(dev, non_blocking=True)
     img_all = torch.empty(world * per, capi.REGIONS, capi.EMBED, device=dev, dtype=torch.bfloat16)
     gram_all = torch.empty(world * per, capi.GRAM_BYTES, device=dev, dtype=torch.uint8)
-    img_loc = img_all[rank * per:(rank + 1) * per]          # all_gather_into_tensor may gather in place
+    img_bytes, gram_bytes = per * capi.REGIONS * capi.EMBED * 2, per * capi.GRAM_BYTES
+    ws = _sym_workspace(group, img_bytes + gram_bytes, dev)
+    if ws is not None:
+        main = torch.cuda.current_stream(dev)
+        if ws["done"] is not None:
+            main.wait_event(ws["done"])                    # the previous gather's last pull from this buffer is over
+        mine = ws["buf"]
+        sym_img = mine[:img_bytes].view(torch.bfloat16).view(per, capi.REGIONS, capi.EMBED)
+        sym_gram = mine[img_bytes: img_bytes + gram_bytes].view(per, capi.GRAM_BYTES)
+        if hi > lo:
+            prepare_images(sl, out=sym_img[: hi - lo], gram=sym_gram[: hi - lo])
+            img_all[lo:hi].copy_(sym_img[: hi - lo])
+            gram_all[lo:hi].copy_(sym_gram[: hi - lo])
+        side = _gather_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            hdl = ws["hdl"]
+            hdl.barrier()                                   # every rank's slice is written
+            all_bytes = img_all.view(torch.uint8).view(world, img_bytes)
+            for step in range(1, world):
+                r = (rank - step) % world
+                n_r = bounds[r][1] - bounds[r][0]
+                if n_r <= 0:
+                    continue
+                src = hdl.get_buffer(r, (img_bytes + gram_bytes,), torch.uint8)
+                all_bytes[r, : n_r * capi.REGIONS * capi.EMBED * 2].copy_(src[: n_r * capi.REGIONS * capi.EMBED * 2])
+                gram_all[r * per: r * per + n_r].view(-1).copy_(src[img_bytes: img_bytes + n_r * capi.GRAM_BYTES])
+            hdl.barrier()                                   # nobody rewrites its slice while a peer still reads it
+            done = torch.cuda.Event()
+            done.record(side)
+        ws["done"] = done
+        for t in (img_all, gram_all):
+            t.record_stream(side)
+        return PreparedImages(img_all[:n_img], gram_all[:n_img], n_img, local_rows=(lo, hi), gathered=done)
+    img_loc = img_all[rank * per:(rank + 1) * per]          # all_gather_into_tensor gathers in place
     gram_loc = gram_all[rank * per:(rank + 1) * per]
     if hi > lo:
-        loc = prepare_images(sl)
-        img_loc[: hi - lo].copy_(loc.images_bf16)
-        gram_loc[: hi - lo].copy_(loc.gram_pack)
+        prepare_images(sl, out=img_loc[: hi - lo], gram=gram_loc[: hi - lo])
     if hi - lo < per:
         img_loc[hi - lo:].zero_()
         gram_loc[hi - lo:].zero_()
-    dist.all_gather_into_tensor(img_all, img_loc, group=group)       # in place: each rank's slice is already where it belongs
+    dist.all_gather_into_tensor(img_all, img_loc, group=group)
     dist.all_gather_into_tensor(gram_all, gram_loc, group=group)
     return PreparedImages(img_all[:n_img], gram_all[:n_img], n_img)
 
@@ -433,10 +539,15 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
         out = torch.empty(pi.n_img, pc.n_cap, device=dev, dtype=torch.float32)
     assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
     with torch.cuda.device(dev):
-        check(capi.lib().itr_scan_t2i_scores_bf16(ptr(pi.images_bf16), ptr(pi.gram_pack), pi.n_img, ptr(pc.words_bf16),
-                                                  ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, norm, agg,
-                                                  float(lambda_softmax), float(lambda_lse), ptr(out),
-                                                  out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))
+        # multi-GPU: this rank's own image rows first, the others once the copy engines have delivered them
+        for lo, hi, needs_gather in pi.row_ranges():
+            if needs_gather:
+                pi.wait_gathered()
+            o = out[lo:hi]
+            check(capi.lib().itr_scan_t2i_scores_bf16(ptr(pi.images_bf16[lo:hi]), ptr(pi.gram_pack[lo:hi]), hi - lo,
+                                                      ptr(pc.words_bf16), ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, norm,
+                                                      agg, float(lambda_softmax), float(lambda_lse), ptr(o),
+                                                      out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))
     return out
 
 
@@ -447,6 +558,7 @@ def scan_t2i_gt_thresholds(pi: PreparedImages, pc: PreparedCaptions, raw_feature
     its captions among THESE captions (-inf if none) -- all-reduce(MAX) it across caption shards before counting."""
     norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
     dev = pi.images_bf16.device
+    pi.wait_gathered()
     thr_row = torch.empty(pi.n_img, device=dev, dtype=torch.float32)
     thr_col = torch.empty(pc.n_cap, device=dev, dtype=torch.float32)
     items, n_items = gt_items(pc, cap_offset, caps_per_img, pi.n_img)
@@ -463,7 +575,8 @@ def scan_t2i_count(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, a
                    thr_row, thr_col, cap_offset=0, out=None):
     """Counting pass of the fused evaluation (itr_scan_t2i_count_bf16): the score kernel compares every score with its
     row / column threshold as it is produced.  Returns (cnt_row i32 (n_img,), cnt_col i32 (n_cap,), best_row u64-as-i64,
-    best_col u64-as-i64) in the formats of rank_count; the score matrix is written only if `out` is given."""
+    best_col u64-as-i64) in the formats of rank_count; the score matrix is written only if `out` is given.
+    Multi-GPU: this rank's own image rows are counted while the other ranks' rows are still arriving."""
     norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
     dev = pi.images_bf16.device
     cnt_row = torch.empty(pi.n_img, device=dev, dtype=torch.int32)
@@ -473,11 +586,16 @@ def scan_t2i_count(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, a
     if out is not None:
         assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
     with torch.cuda.device(dev):
-        check(capi.lib().itr_scan_t2i_count_bf16(ptr(pi.images_bf16), ptr(pi.gram_pack), pi.n_img, ptr(pc.words_bf16),
-                                                 ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, pc.n_cap, norm, agg,
-                                                 float(lambda_softmax), float(lambda_lse), int(cap_offset), ptr(thr_col),
-                                                 ptr(thr_row), ptr(out), out.stride(0) if out is not None else 0,
-                                                 ptr(cnt_row), ptr(cnt_col), ptr(best_row), ptr(best_col), stream_ptr()))
+        for k, (lo, hi, needs_gather) in enumerate(pi.row_ranges()):
+            if needs_gather:
+                pi.wait_gathered()
+            o = out[lo:hi] if out is not None else None
+            check(capi.lib().itr_scan_t2i_count_bf16(ptr(pi.images_bf16[lo:hi]), ptr(pi.gram_pack[lo:hi]), hi - lo,
+                                                     ptr(pc.words_bf16), ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles,
+                                                     pc.n_cap, norm, agg, float(lambda_softmax), float(lambda_lse),
+                                                     int(cap_offset), ptr(thr_col), ptr(thr_row[lo:hi]), ptr(o),
+                                                     out.stride(0) if out is not None else 0, ptr(cnt_row[lo:hi]), ptr(cnt_col),
+                                                     ptr(best_row[lo:hi]), ptr(best_col), int(lo), int(k > 0), stream_ptr()))
     return cnt_row, cnt_col, best_row, best_col
 
 
@@ -558,6 +676,7 @@ def scan_scores_tc_generic(images, captions, cap_lens, cross_attn, raw_feature_n
         raise ValueError("unknown cross_attn: {}".format(cross_attn))
     if pi is None:
         pi = prepare_images(images)
+    pi.wait_gathered()
     ln = lengths_to_numpy(cap_lens, len(cap_lens))
     if len(ln) and (ln.min() < 1 or ln.max() > GENERIC_MAX_WORDS):
         raise ValueError("the two-phase tensor-core path scores captions of 1..{} words, got {}..{}; use the float32 mode "

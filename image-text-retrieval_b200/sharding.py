@@ -71,7 +71,19 @@ class FusedScanStats:
         return _BlockShape(self.pi.n_img, self.pc.n_cap, self.pi.images_bf16.device)
 
     def thresholds(self, block, cap_offset, caps_per_img):
-        return ops.scan_t2i_gt_thresholds(self.pi, self.pc, *self.args, cap_offset=cap_offset, caps_per_img=caps_per_img)
+        pi, n_local = self.pi, self.pc.n_cap
+        if pi.gathered is not None and pi.local_rows is not None:
+            # multi-GPU: the ground-truth images of this rank's captions are (normally) the images it prepared itself,
+            # so the pre-pass does not have to wait for the other ranks' images
+            lo, hi = pi.local_rows
+            g_lo, g_hi = cap_offset // caps_per_img, min(-(-(cap_offset + n_local) // caps_per_img), pi.n_img)
+            if n_local > 0 and lo <= g_lo and g_hi <= hi and cap_offset - lo * caps_per_img >= 0:
+                tr, tc = ops.scan_t2i_gt_thresholds(pi.rows(lo, hi), self.pc, *self.args,
+                                                    cap_offset=cap_offset - lo * caps_per_img, caps_per_img=caps_per_img)
+                thr_row = torch.full((pi.n_img,), float("-inf"), device=tr.device)
+                thr_row[lo:hi] = tr
+                return thr_row, tc
+        return ops.scan_t2i_gt_thresholds(pi, self.pc, *self.args, cap_offset=cap_offset, caps_per_img=caps_per_img)
 
     def count(self, block, thr_row, thr_col, cap_offset):
         cnt_row, cnt_col, best_row, best_col = ops.scan_t2i_count(self.pi, self.pc, *self.args, thr_row, thr_col,

@@ -175,7 +175,9 @@ int itr_scan_epilogue_f32(const float* affinity, int n_img, const int32_t* cap_r
  *   3. itr_scan_t2i_count_bf16: the full pass; every score is compared with its thresholds as it is produced:
  *      cnt_col[c] / cnt_row[i] = #scores strictly above (the t2i rank of caption c / this shard's part of the i2t rank
  *      of image i), best_col / best_row = max of (orderable(score) << 32 | ~index) (index = image / GLOBAL caption).
- *      `scores` may be NULL: the matrix is then never written.
+ *      `scores` may be NULL: the matrix is then never written.  The images may be fed in several launches (a range of
+ *      rows each: pointers advanced to the range, img_offset = its first image, accumulate_columns = 1 from the second
+ *      launch on) -- how the multi-GPU path scores its own image shard while the others are still arriving.
  * Replaces cal_sims + i2t + t2i for SCAN t2i (same feature norms as itr_scan_t2i_scores_bf16). */
 int itr_scan_plan_gt_items(const int32_t* row_meta_host, int n_tiles, int cap_offset, int caps_per_img, int n_img,
                            int32_t* items_host, int max_items, int* n_items);
@@ -188,7 +190,8 @@ int itr_scan_t2i_count_bf16(const uint16_t* images_bf16, const void* gram_pack, 
                             const uint16_t* words_bf16, const int32_t* row_meta, const float* row_wnorm,
                             int n_tiles, int n_cap, int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                             int cap_offset, const float* thr_col, const float* thr_row, float* scores, int64_t ld_scores,
-                            int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col, void* stream);
+                            int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col,
+                            int img_offset, int accumulate_columns, void* stream);
 
 /* Debug / bring-up: raw region-word affinities of ONE (word tile, image tile) pair as the
  * tensor cores produced them: out[128 rows][144 cols] fp32. */

@@ -329,3 +329,40 @@ def test_cal_sims_and_recall_never_builds_the_matrix():
             assert got[k] == want[k], k
     matrix_bytes = n_img * n_cap * 4
     assert peak_matrix - peak_fused >= 0.9 * matrix_bytes, (peak_matrix, peak_fused, matrix_bytes)
+
+
+def test_image_row_ranges_give_the_same_results():
+    """The multi-GPU path scores its own image rows before the other ranks' rows have arrived (PreparedImages.row_ranges):
+    launching the kernels per row range -- scores, ground-truth pre-pass on the local rows only, counting with column
+    accumulation -- must change nothing."""
+    n_img, n_cap = 50, 250
+    img, cap, lens = itr_b200.synth.scan_inputs(n_img, n_cap, 10.5, 41, device="cuda")
+    args = ("clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    pc = ops.prepare_captions(cap, lens)
+    whole = ops.prepare_images(img)
+    want = ops.scan_t2i_scores_bf16(whole, pc, *args)
+    want_ranks = sharding.sharded_ranks(want, 0, n_cap, None, 5)
+
+    def split(lo, hi):
+        pi = ops.prepare_images(img)
+        ev_ = torch.cuda.Event()
+        ev_.record()
+        pi.local_rows, pi.gathered = (lo, hi), ev_
+        return pi
+
+    for lo, hi in ((0, 10), (13, 31), (40, 50), (0, 50)):
+        pi = split(lo, hi)
+        assert [r[:2] for r in pi.row_ranges()][0] == (lo, hi)
+        assert torch.equal(ops.scan_t2i_scores_bf16(pi, pc, *args), want) and pi.gathered is None
+        # captions [5 lo, 5 hi) are this "rank's" shard: their ground-truth images are the local rows
+        c0, c1 = 5 * lo, 5 * hi
+        pc_loc = ops.prepare_captions(cap[c0:c1], lens[c0:c1])
+        stats = sharding.FusedScanStats(split(lo, hi), pc_loc, *args)
+        tr, tc_ = stats.thresholds(stats.block(), c0, 5)
+        assert torch.equal(tc_, want[torch.arange(c0, c1, device="cuda") // 5, torch.arange(c0, c1, device="cuda")])
+        assert torch.isinf(tr[:lo]).all() and torch.isinf(tr[hi:]).all()
+        assert torch.equal(tr[lo:hi], want[lo:hi, c0:c1].view(hi - lo, hi - lo, 5)[torch.arange(hi - lo), torch.arange(hi - lo)].max(dim=1).values)
+        stats = sharding.FusedScanStats(split(lo, hi), pc, *args)
+        got = sharding.sharded_ranks(stats.block(), 0, n_cap, None, 5, stats)
+        for a, b in zip(got, want_ranks):
+            assert torch.equal(a, b)
