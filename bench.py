@@ -261,6 +261,23 @@ def run_side_config(args):
             ci = (0.2 + sc - d.t().expand_as(sc)).clamp(min=0).masked_fill_(eye, 0)
             (cs.max(1)[0].sum() + ci.max(0)[0].sum()).backward()
         us_ours, us_eager = _time_cuda(ours, 300) * 1e3, _time_cuda(eager, 300) * 1e3
+        # the native call alone (one cooperative launch: scores + hinge + both gradients), without autograd bookkeeping,
+        # and replayed from a CUDA graph (device time of the launch itself)
+        im_c, s_c = im.contiguous(), s.contiguous()
+        us_native = _time_cuda(lambda: ops.cosine_hinge(im_c, s_c, 0.2, True), 300) * 1e3
+        us_graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ops.cosine_hinge(im_c, s_c, 0.2, True)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    held = ops.cosine_hinge(im_c, s_c, 0.2, True)
+            torch.cuda.current_stream().wait_stream(side)
+            us_graph = _time_cuda(graph.replay, 300) * 1e3
+        except Exception as exc:      # noqa: BLE001  (informational)
+            us_graph = repr(exc)[:80]
         ac, bc = im.cpu().clone().requires_grad_(True), s.cpu().clone().requires_grad_(True)
         t0 = time.perf_counter()
         for _ in range(50):
@@ -268,6 +285,7 @@ def run_side_config(args):
             ref_port.hinge(ac.mm(bc.t()), 0.2, True).backward()
         cpu = (time.perf_counter() - t0) / 50
         out.update(workload="VSE++ ContrastiveLoss max_violation fwd+bwd, batch 128 x 1024", us_per_call=us_ours,
+                   us_per_call_native_no_autograd=us_native, us_per_call_cuda_graph_replay=us_graph,
                    us_per_call_eager_pytorch_same_gpu=us_eager, us_per_call_cpu_port=cpu * 1e6)
     elif args.config == 6:    # SCAN ContrastiveLoss t2i, max_violation, batch 128, embed 1024, fwd + bwd (row f3)
         lens_np = np.clip(synth.caption_lengths(128, 10.5, 16), 1, 60)

@@ -51,6 +51,7 @@ SIGNATURES = {
     "itr_tc_mma_microbench": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "itr_tc_mma2_microbench": (_i, [_i, _i, _i, _i, _i, _i, _p, _p]),
     "itr_hinge_fwd_bwd_f32": (_i, [_p, _l, _i, _f, _i, _p, _p, _l, _p]),
+    "itr_cosine_hinge_workspace_f32": (_l, [_i, _i]),
     "itr_cosine_hinge_fwd_bwd_f32": (_i, [_p, _p, _i, _i, _f, _i, _p, _p, _p, _p, _p]),
     "itr_rank_thresholds_f32": (_i, [_p, _l, _i, _i, _i, _i, _p, _p, _p]),
     "itr_rank_count_f32": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

@@ -849,12 +849,26 @@ extern "C" int itr_hinge_fwd_bwd_f32(const float* scores, int64_t ld_scores, int
   return ITR_OK;
 }
 
+// one cooperative launch for batches up to 264 (vse_step.cu); 1 = done, 0 = not applicable, < 0 = error in *status
+int vse_step_fused(const float* im, const float* s, int n, int d, float margin, int max_violation, float* ws, float* loss,
+                   float* d_im, float* d_s, cudaStream_t st, int* status);
+
 extern "C" int itr_cosine_hinge_fwd_bwd_f32(const float* im, const float* s, int n, int d, float margin,
                                             int max_violation, float* ws, float* loss, float* d_im, float* d_s,
                                             void* stream) {
   ITR_REQUIRE(im && s && ws && loss, "itr_cosine_hinge_fwd_bwd_f32: null pointer");
   ITR_REQUIRE(n >= 1 && d >= 1, "itr_cosine_hinge_fwd_bwd_f32: bad shape");
   cudaStream_t st = as_stream(stream);
+  {
+    static int use_fused = -1;
+    if (use_fused < 0) { const char* e = getenv("ITR_B200_VSE_STEP"); use_fused = (e && e[0] == 'm') ? 0 : 1; }    // "multi" = round-1 path
+    if (use_fused) {
+      int status = ITR_OK;
+      const int done = vse_step_fused(im, s, n, d, margin, max_violation, ws, loss, d_im, d_s, st, &status);
+      if (done < 0) return status;
+      if (done > 0) return ITR_OK;
+    }
+  }
   float* S = ws;
   float* dS = ws + (int64_t)n * n;
   const bool need_grad = d_im != nullptr || d_s != nullptr;

@@ -753,7 +753,7 @@ def cosine_hinge(im, s, margin, max_violation, need_grad=True):
     if im.shape != s.shape or im.dim() != 2:
         raise ValueError("im and s must both be (batch, d), got {} and {}".format(tuple(im.shape), tuple(s.shape)))
     n, d = im.shape
-    ws = torch.empty(2 * n * n, device=im.device, dtype=torch.float32)
+    ws = torch.empty(max(int(capi.lib().itr_cosine_hinge_workspace_f32(n, d)), 2 * n * n), device=im.device, dtype=torch.float32)
     loss = torch.empty((), device=im.device, dtype=torch.float32)
     d_im = torch.empty_like(im) if need_grad else None
     d_s = torch.empty_like(s) if need_grad else None

@@ -223,7 +223,10 @@ int itr_tc_mma2_microbench(int n_cols, int n_acc, int iters, int a_tmem, int n_i
 int itr_hinge_fwd_bwd_f32(const float* scores, int64_t ld_scores, int n, float margin, int max_violation,
                           float* loss, float* dscores, int64_t ld_dscores, void* stream);
 /* VSE++ training step of the path: scores = im @ s.T, hinge, and the gradients w.r.t. both
- * embedding matrices (d_im = dS @ s, d_s = dS.T @ im).  ws: n*n*2 floats of workspace. */
+ * embedding matrices (d_im = dS @ s, d_s = dS.T @ im).  ws: itr_cosine_hinge_workspace_f32(n, d) floats, 16-byte aligned.
+ * Batches up to 264 with d % 4 == 0 run as ONE cooperative launch (csrc/vse_step.cu: split-K scores, fixed-order
+ * reduction + hinge statistics, gradients, two grid barriers); larger ones as five launches. */
+int64_t itr_cosine_hinge_workspace_f32(int n, int d);
 int itr_cosine_hinge_fwd_bwd_f32(const float* im, const float* s, int n, int d, float margin, int max_violation,
                                  float* ws, float* loss, float* d_im, float* d_s, void* stream);
 

@@ -354,3 +354,23 @@ def test_saem_pdist_measures():
     assert torch.equal(ob.pdist_cos(z, x2.detach()), torch.zeros(2, 23, device="cuda"))     # the reference zeroes 0/0
     crit = ob.ContrastiveLoss(dict(name="SAEM"), margin=0.2, measure="cosine", max_violation=True)
     assert crit.sim is ob.pdist_cos
+
+
+@pytest.mark.parametrize("n,d", [(1, 4), (7, 36), (33, 100), (128, 1024), (200, 2048), (264, 64), (300, 128)])
+def test_fused_vse_step_shapes(n, d):
+    """The one-launch VSE++ step (csrc/vse_step.cu: batches up to 264) against the float64 oracle, for ragged tile /
+    chunk shapes, both hinge modes, with and without gradients; 300 exercises the multi-launch path."""
+    g = torch.Generator().manual_seed(n * 1000 + d)
+    im = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
+    s = torch.nn.functional.normalize(im + 0.5 / d ** 0.5 * torch.randn(n, d, generator=g), dim=-1)
+    sc = so.cosine_scores(im.numpy(), s.numpy())
+    for mv in (True, False):
+        want, dwant = so.hinge_loss(sc, 0.2, mv)
+        loss, d_im, d_s = ops.cosine_hinge(im.cuda(), s.cuda(), 0.2, mv)
+        np.testing.assert_allclose(loss.item(), want, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(d_im.cpu().numpy(), dwant @ s.numpy().astype(np.float64), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(d_s.cpu().numpy(), dwant.T @ im.numpy().astype(np.float64), rtol=1e-4, atol=2e-5)
+        loss2, a2, b2 = ops.cosine_hinge(im.cuda(), s.cuda(), 0.2, mv)             # bit-reproducible
+        assert loss2.item() == loss.item() and torch.equal(a2, d_im) and torch.equal(b2, d_s)
+        loss3, none_a, none_b = ops.cosine_hinge(im.cuda(), s.cuda(), 0.2, mv, need_grad=False)
+        assert loss3.item() == loss.item() and none_a is None and none_b is None
