@@ -353,7 +353,8 @@ def test_image_row_ranges_give_the_same_results():
     for lo, hi in ((0, 10), (13, 31), (40, 50), (0, 50)):
         pi = split(lo, hi)
         assert [r[:2] for r in pi.row_ranges()][0] == (lo, hi)
-        assert torch.equal(ops.scan_t2i_scores_bf16(pi, pc, *args), want) and pi.gathered is None
+        assert torch.equal(ops.scan_t2i_scores_bf16(pi, pc, *args), want)
+        assert pi.gathered is None or (lo, hi) == (0, n_img)        # waited for, unless there was nothing to wait for
         # captions [5 lo, 5 hi) are this "rank's" shard: their ground-truth images are the local rows
         c0, c1 = 5 * lo, 5 * hi
         pc_loc = ops.prepare_captions(cap[c0:c1], lens[c0:c1])
