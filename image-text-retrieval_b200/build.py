@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libitr_b200.so")
-SOURCES = ["simt_kernels.cu", "vse_step.cu", "scan_bwd.cu", "scan_t2i_tc.cu", "scan_t2i_tc2.cu", "tc_microbench2.cu", "plan.cpp"]
-HEADERS = ["common.cuh", "scan_f32.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "itr_b200.h")]
+SOURCES = ["simt_kernels.cu", "vse_step.cu", "scan_bwd.cu", "scan_t2i_tc.cu", "scan_t2i_tc2.cu", "scan_i2t_tc2.cu", "tc_microbench2.cu", "plan.cpp"]
+HEADERS = ["common.cuh", "scan_f32.cuh", "tc_ptx.cuh", "tc2_common.cuh", os.path.join("..", "..", "include", "itr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",

@@ -197,6 +197,9 @@ def _scan(images, captions, cap_lens, config, cross_attn):
                 pi = ops.prepare_images(images)
                 pc = ops.prepare_captions(captions, ln)
                 return ops.scan_t2i_scores_bf16(pi, pc, norm, agg, lam_sm, lam_lse)      # fused tcgen05 kernel
+            if (cross_attn == "i2t" and norm in ("clipped_l2norm", "l2norm")
+                    and os.environ.get("ITR_B200_I2T", "fused") != "twophase"):
+                return ops.scan_i2t_scores_tc(images, captions, ln, norm, agg, lam_sm, lam_lse)   # fused i2t kernel
             if ln.max(initial=0) <= ops.GENERIC_MAX_WORDS:
                 # i2t and the remaining norm modes: tcgen05 affinities + fp32 epilogue (two phases)
                 return ops.scan_scores_tc_generic(images, captions, ln, cross_attn, norm, agg, lam_sm, lam_lse)

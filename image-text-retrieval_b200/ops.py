@@ -283,6 +283,7 @@ class PreparedCaptions:
     sum_len: int
     meta_host: np.ndarray = None  # the same row metadata on the host (the ground-truth item planner reads it)
     plan_key: tuple = None        # identifies the packing (memoised plans)
+    gq_rel: torch.Tensor = None   # (n_tiles, 32, 128) f32 caption-relative word Gram (fused i2t), built on first use
 
 
 TC_MAX_WORDS = 128           # longest caption the fused tcgen05 t2i kernel scores (one 128-row word tile)
@@ -723,6 +724,60 @@ def scan_scores_tc_generic(images, captions, cap_lens, cross_attn, raw_feature_n
                                               ptr(pc.row_wnorm), ptr(region_norm[i0:i1]), ptr(rgram), ptr(cap_gram), ptr(gram_off),
                                               capi.T2I if cross_attn == "t2i" else capi.I2T, norm, agg, float(lambda_softmax),
                                               float(lambda_lse), ptr(out[i0:i1]), out.stride(0), stream_ptr()))
+    return out
+
+
+I2T_FUSED_MAX_WORDS = 32     # longest caption the fused i2t kernel scores (a caption must fit one 32-lane quarter)
+
+
+def caption_gram_rel(pc: PreparedCaptions):
+    """Caption-relative word Gram of the packed tiles (itr_scan_caption_gram_rel_bf16), cached on the PreparedCaptions."""
+    if pc.gq_rel is None:
+        out = torch.empty(max(pc.n_tiles, 1), 32, capi.TILE_WORDS, device=pc.words_bf16.device, dtype=torch.float32)
+        with torch.cuda.device(out.device):
+            check(capi.lib().itr_scan_caption_gram_rel_bf16(ptr(pc.words_bf16), ptr(pc.row_meta), pc.n_tiles, ptr(out), stream_ptr()))
+        pc.gq_rel = out
+    return pc.gq_rel
+
+
+def scan_i2t_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, agg_func, lambda_softmax, lambda_lse,
+                         out=None):
+    """Fused tensor-core i2t scores (itr_scan_i2t_scores_bf16) of every caption of up to 32 words; the columns of longer
+    captions are left untouched (see scan_i2t_scores_tc)."""
+    norm, agg = capi.norm_code(raw_feature_norm), capi.agg_code(agg_func)
+    dev = pi.images_bf16.device
+    pi.wait_gathered()
+    if out is None:
+        out = torch.empty(pi.n_img, pc.n_cap, device=dev, dtype=torch.float32)
+    assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
+    if pi.n_img == 0 or pc.n_cap == 0:
+        return out
+    region_norm = pi.gram_pack[:, 4608:].contiguous().view(torch.float32).sqrt().contiguous()      # |v_k| from the Gram diagonal
+    gq = caption_gram_rel(pc)
+    with torch.cuda.device(dev):
+        check(capi.lib().itr_scan_i2t_scores_bf16(ptr(pi.images_bf16), ptr(region_norm), pi.n_img, ptr(pc.words_bf16),
+                                                  ptr(pc.row_meta), ptr(gq), pc.n_tiles, norm, agg, float(lambda_softmax),
+                                                  float(lambda_lse), ptr(out), out.stride(0), stream_ptr()))
+    return out
+
+
+def scan_i2t_scores_tc(images, captions, cap_lens, raw_feature_norm, agg_func, lambda_softmax, lambda_lse):
+    """i2t scores on the tensor cores for raw_feature_norm in {clipped_l2norm, l2norm}: the fused kernel for captions of up
+    to 32 words; the (rare) longer ones through the two-phase path (<= 100 words) or the float32 kernel."""
+    ln = lengths_to_numpy(cap_lens, len(cap_lens))
+    pi = prepare_images(images)
+    pc = prepare_captions(captions, ln)
+    out = scan_i2t_scores_bf16(pi, pc, raw_feature_norm, agg_func, lambda_softmax, lambda_lse)
+    long_ids = np.nonzero(ln > I2T_FUSED_MAX_WORDS)[0]
+    if len(long_ids):
+        idx = torch.from_numpy(long_ids).to(out.device)
+        caps_long, ln_long = captions[idx], ln[long_ids]
+        if int(ln_long.max()) <= GENERIC_MAX_WORDS:
+            sub = scan_scores_tc_generic(images, caps_long, ln_long, "i2t", raw_feature_norm, agg_func, lambda_softmax,
+                                         lambda_lse, pi=pi)
+        else:
+            sub = scan_scores_f32(images, caps_long, ln_long, "i2t", raw_feature_norm, agg_func, lambda_softmax, lambda_lse)
+        out[:, idx] = sub
     return out
 
 

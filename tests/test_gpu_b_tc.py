@@ -367,3 +367,45 @@ def test_image_row_ranges_give_the_same_results():
         got = sharding.sharded_ranks(stats.block(), 0, n_cap, None, 5, stats)
         for a, b in zip(got, want_ranks):
             assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused i2t kernel (csrc/scan_i2t_tc2.cu)
+@pytest.mark.parametrize("case", ["scan_small", "scan_long"])
+def test_fused_i2t_golden(case):
+    """xattn_score_i2t on the fused tensor-core kernel against the reference's own outputs: both l2 feature norms, all
+    four aggregations (scan_long: every caption is longer than 32 words and takes the two-phase path)."""
+    g = load_golden(case)
+    img = torch.from_numpy(bits_to_f32(g["img_bits"])).cuda()
+    cap = torch.from_numpy(bits_to_f32(g["cap_bits"])).cuda()
+    lens = g["lens"]
+    for norm in ("clipped_l2norm", "l2norm"):
+        for agg in so.AGG_FUNCS:
+            got = ob.xattn_score_i2t(img, cap, lens, cfg(cross_attn="i2t", raw_feature_norm=norm, agg_func=agg, lambda_softmax=4.0))
+            want = g["i2t|{}|{}|f64".format(norm, agg)]
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL_TC, atol=ATOL_TC, err_msg="{} {}".format(norm, agg))
+    if case == "scan_small":
+        pi, pc = ops.prepare_images(img), ops.prepare_captions(cap, lens)
+        a = ops.scan_i2t_scores_bf16(pi, pc, "clipped_l2norm", "Mean", 4.0, 6.0)
+        np.testing.assert_allclose(a.cpu().numpy(), g["i2t|clipped_l2norm|Mean|f64"], rtol=RTOL_TC, atol=ATOL_TC)
+        assert torch.equal(a, ops.scan_i2t_scores_bf16(pi, pc, "clipped_l2norm", "Mean", 4.0, 6.0))      # deterministic
+
+
+@pytest.mark.parametrize("n_img,n_cap,agg", [(37, 185, "Mean"), (130, 333, "LogSumExp"), (5, 64, "Max"), (64, 200, "Sum")])
+def test_fused_i2t_matches_two_phase_and_oracle(n_img, n_cap, agg):
+    lens = itr_b200.synth.caption_lengths(n_cap, 10.5, 7 + n_img)
+    lens[::13] = 32                                  # exactly full quarters
+    lens[5::17] = 1                                  # single-word captions
+    lens[3] = 47                                     # a long caption among short ones: filled by the two-phase path
+    img, cap, lens = itr_b200.synth.scan_inputs(n_img, n_cap, 10.5, 7 + n_img, device="cuda", lengths=lens, round_to="bf16")
+    got = ops.scan_i2t_scores_tc(img, cap, lens, "clipped_l2norm", agg, 4.0, 6.0)
+    two = ops.scan_scores_tc_generic(img, cap, lens, "i2t", "clipped_l2norm", agg, 4.0, 6.0)
+    rel = ((got - two).abs() / two.abs().clamp_min(1e-6)).max().item()
+    assert rel < 1e-3, rel
+    assert torch.equal(got[:, 3], two[:, 3])         # the long caption's column comes from the two-phase path itself
+    sel = np.unique(np.concatenate([np.arange(0, n_cap, max(1, n_cap // 9)), [3, 5, 13]]))
+    sel = sel[sel < n_cap]
+    rows = slice(0, min(n_img, 24))
+    want = so.scan_scores(img[rows].cpu().numpy(), cap[torch.from_numpy(sel).cuda()].cpu().numpy(), lens[sel], "i2t",
+                          "clipped_l2norm", agg, 4.0, 6.0)
+    np.testing.assert_allclose(got[rows][:, torch.from_numpy(sel).cuda()].cpu().numpy(), want, rtol=RTOL_TC, atol=ATOL_TC)
