@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -74,6 +75,11 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f4(uint32_t addr, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ float lds_f1(uint32_t addr) {
   float v;
@@ -222,10 +228,13 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       const int b = it & 1;
       mbar_wait_sleep(afull_bar(b), (it >> 1) & 1);
       int4 meta = make_int4(-1, 0, lane | (lane << 8), 0);
-      if (word_ok) meta = reinterpret_cast<const int4*>(smem + SMEM_AUX + b * AUX_BYTES)[row];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(aempty_bar(b));            // the metadata is in registers: the buffer may be refilled
+      if (word_ok) meta = lds_i4(sbase + SMEM_AUX + b * AUX_BYTES + 16u * (uint32_t)row);
       const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
+      // The buffer may be refilled only once every lane HOLDS its metadata: an arrive issued while the loads are still in
+      // flight lets the refill overtake them (seen as rare stale rows).  The vote consumes every lane's value, and the
+      // arrive depends on its result (lane 31 always ends a caption or is padding, so the mask is never 0).
+      const uint32_t endmask = __ballot_sync(0xffffffffu, lane == seg_hi);
+      if (lane == 0 && endmask != 0u) mbar_arrive(aempty_bar(b));
       const bool long_tile = (meta.z >> 16) & 1;
       const int img = n * IMGS + g;
       const bool valid = img < p.n_img && word_ok && !long_tile;      // warp-uniform
@@ -275,7 +284,6 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       }
       const int len = meta.x >= 0 ? meta.w : 0;
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
-      const uint32_t endmask = __ballot_sync(0xffffffffu, lane == seg_hi);
       tmem_st_wait();
       __syncwarp();
 
