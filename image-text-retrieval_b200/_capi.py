@@ -42,7 +42,7 @@ SIGNATURES = {
     "itr_scan_plan_gt_items": (_i, [_p, _i, _i, _i, _i, _p, _i, C.POINTER(C.c_int)]),
     "itr_scan_t2i_gt_thresholds_bf16": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p]),
     "itr_scan_t2i_count_bf16": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _l, _p, _p, _p, _p, _i, _i, _p]),
-    "itr_scan_caption_gram_rel_bf16": (_i, [_p, _p, _i, _p, _p]),
+    "itr_scan_caption_gram_frag_bf16": (_i, [_p, _p, _i, _p, _p]),
     "itr_scan_i2t_scores_bf16": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _f, _f, _p, _l, _p]),
     "itr_scan_affinity_bf16": (_i, [_p, _i, _p, _i, _p, _p]),
     "itr_scan_caption_gram_f32": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),

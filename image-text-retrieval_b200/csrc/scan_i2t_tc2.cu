@@ -9,18 +9,19 @@
 //     Z_k = sum_j e,  P_k = sum_j e A,  Q_k = sum_j e[j][k] U[j][k],  U[j][k] = sum_j' G_c[j][j'] e[j'][k]
 //     r_k      = P_k / max(|v_k| sqrt(Q_k), 1e-8 Z_k)        cos(v_k, sum_j alpha_kj w_j) with |ctx|^2 = alpha^T G_c alpha
 //     S[i][c]  = aggregate over the 36 regions               LSE / Mean / Max / Sum
-// G_c = W_c W_c^T is the caption's word Gram (fp32, from the bf16-rounded words), handed in "caption-relative" form
-// gq_rel[tile][d][row] = w_row . w_(d-th word of row's caption) (0 beyond the caption) so that lanes read it coalesced.
+// G_c = W_c W_c^T is the caption's word Gram (fp32 accumulation over the bf16-rounded words, rounded to tf32), handed in
+// the fragment order of the contraction below (caption_gram_frag_kernel).
 //
 // Where t2i reduces over regions (in-thread, TMEM lane = word) and needs one cross-lane sum per region, i2t needs three
 // (Z, P, Q) plus the contraction with G_c.  Per (warp = 32 word rows, image), with two 4.6 KB shared-memory scratches:
-//   1. e -> scratch ES (fp32, [row][36]); t = e A is parked in spare tensor-memory columns;
-//   2. U by ONE loop over the caption's words (a coalesced Gram value requested a step ahead, nine 16-byte broadcast reads
-//      of the partner row's e, 36 FMAs per step); y = e U; then for each third of the regions (12): rows (t, y | e) ->
-//      scratch WK and 18 lanes walk the 32 rows restarting at caption ends (the row walk of the t2i kernel, three
-//      quantities at once) and leave the caption's totals P | Q | Z in its last row; the lane of that last word finishes
-//      r_k for the twelve regions and folds them into its aggregate -- one scalar per caption, in a register, is all that
-//      survives between the thirds;
+//   1. e (rounded to tf32, the same value everywhere) -> scratch ES (fp32, [row][36]); t = e A is parked in spare
+//      tensor-memory columns;
+//   2. U = G e on the warp's own tensor cores: mma.sync m16n8k8 tf32, A = the quarter's block-diagonal Gram (eight
+//      coalesced 16-byte loads per lane), B = e from ES, 40 MMAs; y = e U at the accumulator positions; then for each half
+//      of the regions (18): rows (t | y) -> scratch WK and 27 lanes walk the 32 rows of WK and, for Z, of ES in place,
+//      restarting at caption ends (the row walk of the t2i kernel) and leave the caption's totals P | Q | Z in its last
+//      row; the lane of that last word finishes r_k for the eighteen regions and folds them into its aggregate -- one
+//      scalar per caption, in a register, is all that survives between the halves;
 //   3. that lane turns the aggregate into the score and stores it.
 // Main loop, barriers and cluster protocol: scan_t2i_tc2.cu (no Gram MMA, no parking: the accumulator is free again as
 // soon as the 32 epilogue warps of the pair have loaded it).
@@ -60,7 +61,7 @@ static_assert(SMEM_AUX % 16 == 0 && SMEM_ES % 16 == 0 && SMEM_WK % 16 == 0 && SM
 
 struct Params {
   const int4* row_meta;        // [n_wt*128]
-  const float* gq_rel;         // [n_wt][32][128] caption-relative word Gram
+  const float* gq_frag;        // [n_wt][4][2][4][32] float4: word Gram in mma.sync fragment order
   const float* vnorm;          // [n_img][36] region norms
   int n_img, n_wt, n_wp, n_it;
   int agg;
@@ -81,6 +82,26 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
   asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// D (16x8, f32) += A (16x8, row) * B (8x8, col), tf32 operands held as f32 bit patterns
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+#define TMEM_LD_X16(taddr, v, o)                                                                                     \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=f"(v[o + 0]), "=f"(v[o + 1]), "=f"(v[o + 2]), "=f"(v[o + 3]), "=f"(v[o + 4]), "=f"(v[o + 5]),      \
+                 "=f"(v[o + 6]), "=f"(v[o + 7]), "=f"(v[o + 8]), "=f"(v[o + 9]), "=f"(v[o + 10]), "=f"(v[o + 11]),    \
+                 "=f"(v[o + 12]), "=f"(v[o + 13]), "=f"(v[o + 14]), "=f"(v[o + 15])                                   \
+               : "r"(taddr))
+#define TMEM_LD_X2(taddr, v, o) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(v[o + 0]), "=f"(v[o + 1]) : "r"(taddr))
 __device__ __forceinline__ float lds_f1(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -267,7 +288,7 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         for (int i = 0; i < 4; ++i) {
           const float raw = A[k + i];
           const float a = CLIPPED ? fmaxf(raw, 0.1f * raw) : raw;
-          e[i] = ex2f(fmaf(a, cw, shift));
+          e[i] = round_tf32(ex2f(fmaf(a, cw, shift)));      // the tensor-core contraction below reads e as tf32: use the same e everywhere
           A[k + i] = e[i] * raw;                           // t
         }
         sts_f4(myrow + 4 * k, e[0], e[1], e[2], e[3]);
@@ -282,73 +303,87 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         TMEM_ST_X16(tpark + 16, tv, 16);
         TMEM_ST_X4(tpark + 32, tv, 32);
       }
-      const int len = meta.x >= 0 ? meta.w : 0;
-      const int maxlen = __reduce_max_sync(0xffffffffu, len);
       tmem_st_wait();
       __syncwarp();
 
-      // ---- 2a. U[j][k] = sum over the caption's words j' of G_c[j][j'] e[j'][k], all 36 regions: one coalesced Gram value
-      // and nine 16-byte broadcast reads of the partner row per step; the next step's Gram value is requested a step ahead
-      float U[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) U[k] = 0.f;
+      // ---- 2a. U[j][k] = sum over the caption's words j' of G_c[j][j'] e[j'][k] on the warp's own tensor cores: the
+      // quarter's 32x32 block-diagonal Gram (A, pre-arranged in fragment order and tf32-rounded by the Gram kernel) times
+      // e (B, read straight from ES), mma.sync m16n8k8 tf32 -> 2 x 5 accumulator fragments (columns 36..39 are padding).
+      // Within a k-step the contraction index is permuted (logical k = a -> word 8s+2a, k = a+4 -> word 8s+2a+1, the same
+      // in A and B) so that the B reads are free of bank conflicts at the 36-float row pitch.
+      const int fa = lane & 3, fg = lane >> 2;
+      float y[2][5][4];
       {
-        const float* gq = p.gq_rel + (size_t)m * (32 * BLOCK_M) + row;
-        float gv = maxlen > 0 ? gq[0] : 0.f;
-#pragma unroll 1
-        for (int dlt = 0; dlt < maxlen; ++dlt) {
-          const float gnext = dlt + 1 < maxlen ? gq[(dlt + 1) * BLOCK_M] : 0.f;
-          const uint32_t src = es + (uint32_t)min(seg_lo + dlt, 31) * ROW_BYTES;
-          // two reads in flight: the next 16 bytes are requested before the FMAs of the current ones
-          float4 cur = lds_f4(src);
+        const float4* gf = reinterpret_cast<const float4*>(p.gq_frag) + ((size_t)(m * 4 + q) * 8) * 32 + lane;
+        float4 ga[8];
 #pragma unroll
-          for (int c4 = 0; c4 < R / 4; ++c4) {
-            float4 nxt = cur;
-            if (c4 + 1 < R / 4) nxt = lds_f4(src + 16 * (c4 + 1));
-            U[4 * c4 + 0] = fmaf(gv, cur.x, U[4 * c4 + 0]); U[4 * c4 + 1] = fmaf(gv, cur.y, U[4 * c4 + 1]);
-            U[4 * c4 + 2] = fmaf(gv, cur.z, U[4 * c4 + 2]); U[4 * c4 + 3] = fmaf(gv, cur.w, U[4 * c4 + 3]);
-            cur = nxt;
+        for (int i = 0; i < 8; ++i) ga[i] = __ldg(gf + i * 32);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[mt][nt][i] = 0.f;
+        const uint32_t bbase = es + (uint32_t)(2 * fa) * ROW_BYTES + 4u * (uint32_t)fg;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          float b0[5], b1[5];
+#pragma unroll
+          for (int nt = 0; nt < 5; ++nt) {
+            b0[nt] = lds_f1(bbase + (uint32_t)(8 * s * ROW_BYTES + 32 * nt));
+            b1[nt] = lds_f1(bbase + (uint32_t)((8 * s + 1) * ROW_BYTES + 32 * nt));
           }
-          gv = gnext;
-        }
-        // y = e U (this word's own e from its ES row)
 #pragma unroll
-        for (int c4 = 0; c4 < R / 4; ++c4) {
-          const float4 e4 = lds_f4(myrow + 16 * c4);
-          U[4 * c4 + 0] *= e4.x; U[4 * c4 + 1] *= e4.y; U[4 * c4 + 2] *= e4.z; U[4 * c4 + 3] *= e4.w;
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) mma_tf32(y[mt][nt], ga[mt * 4 + s], b0[nt], b1[nt]);
         }
+        // y = e U at the accumulator positions: rows 16 mt + 8 h + fg, columns 8 nt + 2 fa (+1)
+        const uint32_t ebase = es + (uint32_t)fg * ROW_BYTES + 8u * (uint32_t)fa;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+              const float2 e2 = lds_f2(ebase + (uint32_t)((16 * mt + 8 * h) * ROW_BYTES + 32 * nt));
+              y[mt][nt][2 * h] *= e2.x; y[mt][nt][2 * h + 1] *= e2.y;
+            }
       }
 
       // per-caption aggregate over the regions, held by the lane of the caption's last word
       const bool end_lane = lane == seg_hi && meta.x >= 0;
       float aggacc = agg_identity;
 #pragma unroll
-      for (int T = 0; T < 3; ++T) {
-        // ---- 2b. this word's row of the walk scratch, twelve regions: [t | y | e] -----------------------------------
+      for (int H = 0; H < 2; ++H) {
+        // ---- 2b. walk scratch rows for eighteen regions: [t | y]; e is walked in place in ES -----------------------------
         {
-          float t[12];
-          TMEM_LD_X4(tpark + 12 * T, t, 0);
-          TMEM_LD_X4(tpark + 12 * T + 4, t, 4);
-          TMEM_LD_X4(tpark + 12 * T + 8, t, 8);
-          const uint32_t own = myrow + 48u * T;
-          const float4 e0 = lds_f4(own), e1 = lds_f4(own + 16), e2 = lds_f4(own + 32);
-          const uint32_t dst = wk + (uint32_t)lane * ROW_BYTES;
-          sts_f4(dst + 48, U[12 * T + 0], U[12 * T + 1], U[12 * T + 2], U[12 * T + 3]);
-          sts_f4(dst + 64, U[12 * T + 4], U[12 * T + 5], U[12 * T + 6], U[12 * T + 7]);
-          sts_f4(dst + 80, U[12 * T + 8], U[12 * T + 9], U[12 * T + 10], U[12 * T + 11]);
-          sts_f4(dst + 96, e0.x, e0.y, e0.z, e0.w);
-          sts_f4(dst + 112, e1.x, e1.y, e1.z, e1.w);
-          sts_f4(dst + 128, e2.x, e2.y, e2.z, e2.w);
+          float t[18];
+          TMEM_LD_X16(tpark + 18 * H, t, 0);
+          TMEM_LD_X2(tpark + 18 * H + 16, t, 16);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int nt = 2 * H; nt < 2 * H + 3; ++nt) {
+                const int rel = 8 * nt + 2 * fa - 18 * H;           // column pair within the half (even)
+                if (rel >= 0 && rel < 18)
+                  sts_f2(wk + (uint32_t)((16 * mt + 8 * h + fg) * ROW_BYTES + 72 + 4 * rel), y[mt][nt][2 * h], y[mt][nt][2 * h + 1]);
+              }
           tmem_ld_wait();
+          const uint32_t dst = wk + (uint32_t)lane * ROW_BYTES;
           sts_f4(dst, t[0], t[1], t[2], t[3]);
           sts_f4(dst + 16, t[4], t[5], t[6], t[7]);
           sts_f4(dst + 32, t[8], t[9], t[10], t[11]);
+          sts_f4(dst + 48, t[12], t[13], t[14], t[15]);
+          sts_f2(dst + 64, t[16], t[17]);
         }
         __syncwarp();
-        // ---- 2c. row walk (as in the t2i kernel): 18 lanes, two columns each, restart at every caption end and leave the
-        // caption's totals (P | Q | Z for the twelve regions) in its last row ------------------------------------------
-        if (lane < 18) {
-          const uint32_t col = wk + 8u * (uint32_t)lane;
+        // ---- 2c. row walk (as in the t2i kernel): 27 lanes, two columns each (18 on the scratch: P and Q, 9 on ES: Z),
+        // restart at every caption end and leave the caption's totals in its last row -------------------------------------
+        if (lane < 27) {
+          const uint32_t col = lane < 18 ? wk + 8u * (uint32_t)lane : es + (uint32_t)(72 * H) + 8u * (uint32_t)(lane - 18);
           float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 1
           for (int j0 = 0; j0 < 32; j0 += 8) {
@@ -368,23 +403,20 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
           }
         }
         __syncwarp();
-        // ---- 2d. the lane of each caption's last word finishes r_k for the twelve regions and folds them into its
+        // ---- 2d. the lane of each caption's last word finishes r_k for the eighteen regions and folds them into its
         // aggregate: r_k = P_k / max(|v_k| sqrt(Q_k), 1e-8 Z_k) -------------------------------------------------------
         if (end_lane) {
-          const uint32_t tot = wk + (uint32_t)lane * ROW_BYTES;
-          const float4* vn4 = reinterpret_cast<const float4*>(p.vnorm + (size_t)img * R + 12 * T);
+          const uint32_t tw = wk + (uint32_t)lane * ROW_BYTES, te = es + (uint32_t)lane * ROW_BYTES + (uint32_t)(72 * H);
+          const float2* vn2 = reinterpret_cast<const float2*>(p.vnorm + (size_t)img * R + 18 * H);
 #pragma unroll
-          for (int c4 = 0; c4 < 3; ++c4) {
-            const float4 P4 = lds_f4(tot + 16 * c4), Q4 = lds_f4(tot + 48 + 16 * c4), Z4 = lds_f4(tot + 96 + 16 * c4);
-            const float4 v4 = vn4[c4];
-            const float Pv[4] = {P4.x, P4.y, P4.z, P4.w}, Qv[4] = {Q4.x, Q4.y, Q4.z, Q4.w}, Zv[4] = {Z4.x, Z4.y, Z4.z, Z4.w};
-            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float r = __fdividef(Pv[i], fmaxf(vv[i] * sqrtf(fmaxf(Qv[i], 0.f)), 1e-8f * Zv[i]));
-              if (p.agg == ITR_AGG_MAX) aggacc = fmaxf(aggacc, r);
-              else aggacc += (p.agg == ITR_AGG_LSE) ? ex2f(r * p.c_lse) : r;
-            }
+          for (int c = 0; c < 9; ++c) {
+            const float2 P2 = lds_f2(tw + 8 * c), Q2 = lds_f2(tw + 72 + 8 * c), Z2 = lds_f2(te + 8 * c);
+            const float2 v2 = __ldg(vn2 + c);
+            const float r0 = __fdividef(P2.x, fmaxf(v2.x * sqrtf(fmaxf(Q2.x, 0.f)), 1e-8f * Z2.x));
+            const float r1 = __fdividef(P2.y, fmaxf(v2.y * sqrtf(fmaxf(Q2.y, 0.f)), 1e-8f * Z2.y));
+            if (p.agg == ITR_AGG_MAX) aggacc = fmaxf(aggacc, fmaxf(r0, r1));
+            else if (p.agg == ITR_AGG_LSE) aggacc += ex2f(r0 * p.c_lse) + ex2f(r1 * p.c_lse);
+            else aggacc += r0 + r1;
           }
         }
         __syncwarp();
@@ -409,39 +441,48 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
   }
 }
 
-// Caption-relative word Gram of every packed word tile: out[tile][d][row] = w_row . w_(first row of row's caption + d)
-// for d < caption length, else 0 (padding rows: 0).  One warp per word row; the row stays in registers (bf16 pairs).
+// Word Gram of every packed word tile in the order the fused kernel's mma.sync A operand wants it.  Per 32-row quarter the
+// Gram is block-diagonal (G[j][j'] = w_j . w_j' for two words of the same caption, else 0); out[tile][quarter][mt][s][lane]
+// is the float4 (a0..a3) of the m16n8k8 fragment of rows 16 mt .. +15 and k-step s, with the kernel's permutation of the
+// contraction index: a0 = G[16mt+g][8s+2a], a1 = G[16mt+g+8][8s+2a], a2 = G[16mt+g][8s+2a+1], a3 = G[16mt+g+8][8s+2a+1]
+// (g = lane / 4, a = lane % 4), rounded to tf32.  One warp per word row; the row stays in registers (bf16 pairs).
 __global__ void __launch_bounds__(256)
-caption_gram_rel_kernel(const uint16_t* __restrict__ words, const int4* __restrict__ row_meta, int n_tiles, float* __restrict__ out) {
+caption_gram_frag_kernel(const uint16_t* __restrict__ words, const int4* __restrict__ row_meta, int n_tiles, float* __restrict__ out) {
   const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile_out = out + (size_t)tile * (32 * BLOCK_M);
+  for (int i = threadIdx.x; i < 32 * BLOCK_M / 4; i += 256) reinterpret_cast<float4*>(tile_out)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
   for (int r = warp; r < BLOCK_M; r += 8) {
     const size_t row = (size_t)tile * BLOCK_M + r;
     const int4 meta = row_meta[row];
     const int len = (meta.x >= 0 && !((meta.z >> 16) & 1)) ? meta.w : 0;       // long tiles are not scored by the fused kernel
-    float* dst = out + ((size_t)tile * 32) * BLOCK_M + r;
+    if (len == 0) continue;
+    const int q = r >> 5, jl = r & 31, seg_lo = meta.z & 0xff;
     uint4 mine[4];                                                             // 1024 bf16 = 32 lanes x 4 x 8
-    if (len > 0) {
+    {
       const uint4* src = reinterpret_cast<const uint4*>(words + row * D);
 #pragma unroll
       for (int v = 0; v < 4; ++v) mine[v] = src[lane + 32 * v];
     }
-    for (int dlt = 0; dlt < 32; ++dlt) {
+    for (int dlt = 0; dlt < len; ++dlt) {
       float s = 0.f;
-      if (dlt < len) {
-        const uint4* oth = reinterpret_cast<const uint4*>(words + (row - meta.y + dlt) * D);
+      const uint4* oth = reinterpret_cast<const uint4*>(words + (row - meta.y + dlt) * D);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 o = oth[lane + 32 * v];
-          const uint32_t a[4] = {mine[v].x, mine[v].y, mine[v].z, mine[v].w}, bb[4] = {o.x, o.y, o.z, o.w};
+      for (int v = 0; v < 4; ++v) {
+        const uint4 o = oth[lane + 32 * v];
+        const uint32_t a[4] = {mine[v].x, mine[v].y, mine[v].z, mine[v].w}, bb[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            s = fmaf(__uint_as_float(a[w] << 16), __uint_as_float(bb[w] << 16), s);
-            s = fmaf(__uint_as_float(a[w] & 0xffff0000u), __uint_as_float(bb[w] & 0xffff0000u), s);
-          }
+        for (int w = 0; w < 4; ++w) {
+          s = fmaf(__uint_as_float(a[w] << 16), __uint_as_float(bb[w] << 16), s);
+          s = fmaf(__uint_as_float(a[w] & 0xffff0000u), __uint_as_float(bb[w] & 0xffff0000u), s);
         }
-        s = warp_sum(s);
       }
-      if (lane == 0) dst[(size_t)dlt * BLOCK_M] = s;
+      s = warp_sum(s);
+      if (lane == 0) {
+        const int jp = seg_lo + dlt;                                           // quarter-local index of the partner word
+        const int mt = jl >> 4, g = jl & 7, hrow = (jl >> 3) & 1, ks = jp >> 3, a = (jp & 7) >> 1, odd = jp & 1;
+        tile_out[((((q * 2 + mt) * 4 + ks) * 32) + 4 * g + a) * 4 + hrow + 2 * odd] = round_tf32(s);
+      }
     }
   }
 }
@@ -477,21 +518,21 @@ static int launch(const CUtensorMap& map_w, const CUtensorMap& map_i, const Para
 
 using namespace itr;
 
-extern "C" int itr_scan_caption_gram_rel_bf16(const uint16_t* words_bf16, const int32_t* row_meta, int n_tiles, float* gq_rel,
+extern "C" int itr_scan_caption_gram_frag_bf16(const uint16_t* words_bf16, const int32_t* row_meta, int n_tiles, float* gq_frag,
                                               void* stream) {
-  ITR_REQUIRE(words_bf16 && row_meta && gq_rel && n_tiles >= 0, "itr_scan_caption_gram_rel_bf16: bad arguments");
-  ITR_REQUIRE(((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)row_meta & 15) == 0, "itr_scan_caption_gram_rel_bf16: buffers must be 16-byte aligned");
+  ITR_REQUIRE(words_bf16 && row_meta && gq_frag && n_tiles >= 0, "itr_scan_caption_gram_frag_bf16: bad arguments");
+  ITR_REQUIRE(((uintptr_t)words_bf16 & 15) == 0 && ((uintptr_t)row_meta & 15) == 0, "itr_scan_caption_gram_frag_bf16: buffers must be 16-byte aligned");
   if (n_tiles == 0) return ITR_OK;
-  tc2i::caption_gram_rel_kernel<<<n_tiles, 256, 0, as_stream(stream)>>>(words_bf16, reinterpret_cast<const int4*>(row_meta), n_tiles, gq_rel);
+  tc2i::caption_gram_frag_kernel<<<n_tiles, 256, 0, as_stream(stream)>>>(words_bf16, reinterpret_cast<const int4*>(row_meta), n_tiles, gq_frag);
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }
 
 extern "C" int itr_scan_i2t_scores_bf16(const uint16_t* images_bf16, const float* region_norm, int n_img,
-                                        const uint16_t* words_bf16, const int32_t* row_meta, const float* gq_rel, int n_tiles,
+                                        const uint16_t* words_bf16, const int32_t* row_meta, const float* gq_frag, int n_tiles,
                                         int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                                         float* scores, int64_t ld_scores, void* stream) {
-  ITR_REQUIRE(images_bf16 && region_norm && words_bf16 && row_meta && gq_rel && scores, "itr_scan_i2t_scores_bf16: null pointer");
+  ITR_REQUIRE(images_bf16 && region_norm && words_bf16 && row_meta && gq_frag && scores, "itr_scan_i2t_scores_bf16: null pointer");
   ITR_REQUIRE(feature_norm == ITR_NORM_CLIPPED_L2 || feature_norm == ITR_NORM_L2,
               "itr_scan_i2t_scores_bf16: raw_feature_norm %d is only available in the two-phase / float32 paths", feature_norm);
   ITR_REQUIRE(agg >= 0 && agg <= ITR_AGG_SUM, "unknown aggfunc: %d", agg);
@@ -511,7 +552,7 @@ extern "C" int itr_scan_i2t_scores_bf16(const uint16_t* images_bf16, const float
   if (rc) return rc;
   tc2i::Params p{};
   p.row_meta = reinterpret_cast<const int4*>(row_meta);
-  p.gq_rel = gq_rel; p.vnorm = region_norm;
+  p.gq_frag = gq_frag; p.vnorm = region_norm;
   p.n_img = n_img; p.n_wt = n_tiles; p.n_wp = (n_tiles + 1) / 2; p.n_it = (n_img + tc2::IMGS - 1) / tc2::IMGS;
   p.agg = agg;
   p.c_sm = lambda_softmax * 1.4426950408889634f;

@@ -283,7 +283,7 @@ class PreparedCaptions:
     sum_len: int
     meta_host: np.ndarray = None  # the same row metadata on the host (the ground-truth item planner reads it)
     plan_key: tuple = None        # identifies the packing (memoised plans)
-    gq_rel: torch.Tensor = None   # (n_tiles, 32, 128) f32 caption-relative word Gram (fused i2t), built on first use
+    gq_frag: torch.Tensor = None  # (n_tiles, 32, 128) f32 word Gram in mma fragment order (fused i2t), built on first use
 
 
 TC_MAX_WORDS = 128           # longest caption the fused tcgen05 t2i kernel scores (one 128-row word tile)
@@ -730,14 +730,14 @@ def scan_scores_tc_generic(images, captions, cap_lens, cross_attn, raw_feature_n
 I2T_FUSED_MAX_WORDS = 32     # longest caption the fused i2t kernel scores (a caption must fit one 32-lane quarter)
 
 
-def caption_gram_rel(pc: PreparedCaptions):
-    """Caption-relative word Gram of the packed tiles (itr_scan_caption_gram_rel_bf16), cached on the PreparedCaptions."""
-    if pc.gq_rel is None:
+def caption_gram_frag(pc: PreparedCaptions):
+    """Word Gram of the packed tiles in mma fragment order (itr_scan_caption_gram_frag_bf16), cached on the PreparedCaptions."""
+    if pc.gq_frag is None:
         out = torch.empty(max(pc.n_tiles, 1), 32, capi.TILE_WORDS, device=pc.words_bf16.device, dtype=torch.float32)
         with torch.cuda.device(out.device):
-            check(capi.lib().itr_scan_caption_gram_rel_bf16(ptr(pc.words_bf16), ptr(pc.row_meta), pc.n_tiles, ptr(out), stream_ptr()))
-        pc.gq_rel = out
-    return pc.gq_rel
+            check(capi.lib().itr_scan_caption_gram_frag_bf16(ptr(pc.words_bf16), ptr(pc.row_meta), pc.n_tiles, ptr(out), stream_ptr()))
+        pc.gq_frag = out
+    return pc.gq_frag
 
 
 def scan_i2t_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, agg_func, lambda_softmax, lambda_lse,
@@ -753,7 +753,7 @@ def scan_i2t_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
     if pi.n_img == 0 or pc.n_cap == 0:
         return out
     region_norm = pi.gram_pack[:, 4608:].contiguous().view(torch.float32).sqrt().contiguous()      # |v_k| from the Gram diagonal
-    gq = caption_gram_rel(pc)
+    gq = caption_gram_frag(pc)
     with torch.cuda.device(dev):
         check(capi.lib().itr_scan_i2t_scores_bf16(ptr(pi.images_bf16), ptr(region_norm), pi.n_img, ptr(pc.words_bf16),
                                                   ptr(pc.row_meta), ptr(gq), pc.n_tiles, norm, agg, float(lambda_softmax),

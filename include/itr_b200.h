@@ -165,13 +165,14 @@ int itr_scan_epilogue_f32(const float* affinity, int n_img, const int32_t* cap_r
  * xattn_score_i2t (Objectives.py:376-417) for raw_feature_norm in {clipped_l2norm, l2norm}, every agg_func.  Operands as
  * for itr_scan_t2i_scores_bf16 (same plan / pack / image prep) plus
  *   region_norm [n_img][36] f32: |v_k| of the (rounded) regions (the square roots of the Gram pack's diagonal);
- *   gq_rel [n_tiles][32][128] f32 from itr_scan_caption_gram_rel_bf16: the word Gram of every caption in caption-relative
- *          form, gq_rel[tile][d][row] = w_row . w_(d-th word of row's caption), 0 beyond the caption.
+ *   gq_frag [n_tiles][4096] f32 from itr_scan_caption_gram_frag_bf16: per 32-row quarter the block-diagonal word Gram
+ *          (w_j . w_j' for two words of the same caption, else 0; fp32 accumulation, rounded to tf32) in the fragment
+ *          order of the kernel's mma.sync A operand -- an opaque companion of the packed words, valid for the same plan.
  * Captions of more than 32 words (the planner's `long` tiles) are NOT scored: their columns of `scores` are left
  * untouched for the two-phase path (itr_scan_affinity_bf16 + itr_scan_epilogue_f32) to fill. */
-int itr_scan_caption_gram_rel_bf16(const uint16_t* words_bf16, const int32_t* row_meta, int n_tiles, float* gq_rel, void* stream);
+int itr_scan_caption_gram_frag_bf16(const uint16_t* words_bf16, const int32_t* row_meta, int n_tiles, float* gq_frag, void* stream);
 int itr_scan_i2t_scores_bf16(const uint16_t* images_bf16, const float* region_norm, int n_img,
-                             const uint16_t* words_bf16, const int32_t* row_meta, const float* gq_rel, int n_tiles,
+                             const uint16_t* words_bf16, const int32_t* row_meta, const float* gq_frag, int n_tiles,
                              int feature_norm, int agg, float lambda_softmax, float lambda_lse,
                              float* scores, int64_t ld_scores, void* stream);
 

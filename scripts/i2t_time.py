@@ -18,8 +18,8 @@ def t(fn, n=5):
     return e0.elapsed_time(e1) / n
 out = torch.empty(1000, 5000, device="cuda")
 print("fused i2t kernel      %.3f ms" % t(lambda: ops.scan_i2t_scores_bf16(pi, pc, "clipped_l2norm", "Mean", 4.0, 6.0, out=out)))
-pc.gq_rel = None
-print("caption gram (rel)    %.3f ms" % t(lambda: (setattr(pc, "gq_rel", None), ops.caption_gram_rel(pc))))
+pc.gq_frag = None
+print("caption gram (rel)    %.3f ms" % t(lambda: (setattr(pc, "gq_frag", None), ops.caption_gram_frag(pc))))
 print("t2i kernel (same shape) %.3f ms" % t(lambda: ops.scan_t2i_scores_bf16(pi, pc, "clipped_l2norm", "LogSumExp", 9.0, 6.0, out=out)))
 print("two-phase i2t         %.3f ms" % t(lambda: ops.scan_scores_tc_generic(img, cap, ln, "i2t", "clipped_l2norm", "Mean", 4.0, 6.0, pi=pi, pc=pc), 3))
 print("whole scan_i2t_scores_tc %.3f ms" % t(lambda: ops.scan_i2t_scores_tc(img, cap, ln, "clipped_l2norm", "Mean", 4.0, 6.0), 3))

@@ -401,7 +401,7 @@ def test_fused_i2t_matches_two_phase_and_oracle(n_img, n_cap, agg):
     got = ops.scan_i2t_scores_tc(img, cap, lens, "clipped_l2norm", agg, 4.0, 6.0)
     two = ops.scan_scores_tc_generic(img, cap, lens, "i2t", "clipped_l2norm", agg, 4.0, 6.0)
     rel = ((got - two).abs() / two.abs().clamp_min(1e-6)).max().item()
-    assert rel < 1e-3, rel
+    assert rel < 2e-3, rel                           # two approximations, each within RTOL_TC of the oracle (below)
     assert torch.equal(got[:, 3], two[:, 3])         # the long caption's column comes from the two-phase path itself
     sel = np.unique(np.concatenate([np.arange(0, n_cap, max(1, n_cap // 9)), [3, 5, 13]]))
     sel = sel[sel < n_cap]
