@@ -51,7 +51,8 @@ constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_ES = SMEM_AUX + 2 * AUX_BYTES;
 constexpr int SMEM_WK = SMEM_ES + NUM_EPI_WARPS * WARP_SCRATCH;
-constexpr int SMEM_BARS = SMEM_WK + NUM_EPI_WARPS * WARP_SCRATCH;
+constexpr int SMEM_LIST = SMEM_WK + NUM_EPI_WARPS * WARP_SCRATCH;       // per warp: rows of its caption ends, 32 bytes
+constexpr int SMEM_BARS = SMEM_LIST + NUM_EPI_WARPS * 32;
 constexpr int NUM_BARS = 2 * STAGES + 8;
 constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
@@ -81,6 +82,19 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
   int4 v;
   asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
@@ -237,6 +251,7 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t es = sbase + SMEM_ES + (uint32_t)(warp - EPI_WARP0) * WARP_SCRATCH;
     const uint32_t wk = sbase + SMEM_WK + (uint32_t)(warp - EPI_WARP0) * WARP_SCRATCH;
+    const uint32_t endlist = sbase + SMEM_LIST + (uint32_t)(warp - EPI_WARP0) * 32;
     const uint32_t tpark = tmem_base + 2 * ACC_PITCH + 56 * g + lane_sel;      // 36 of the group's 56 spare TMEM columns
     const float shift = -fabsf(p.c_sm);
     const float agg_identity = (p.agg == ITR_AGG_MAX) ? -INFINITY : 0.f;
@@ -303,6 +318,18 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         TMEM_ST_X16(tpark + 16, tv, 16);
         TMEM_ST_X4(tpark + 32, tv, 32);
       }
+      // the quarter's Gram fragments (step 2a) are requested as soon as t has left the registers
+      float4 ga[8];
+      {
+        const float4* gf = reinterpret_cast<const float4*>(p.gq_frag) + ((size_t)(m * 4 + q) * 8) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ga[i] = __ldg(gf + i * 32);
+      }
+      // rows of the (real) caption ends, in order: the pairs (caption end, region) of step 2d are dealt to the lanes
+      const bool end_lane = lane == seg_hi && meta.x >= 0;
+      const uint32_t endv = __ballot_sync(0xffffffffu, end_lane);
+      const int npairs = __popc(endv) * 18;
+      if (end_lane) sts_u8(endlist + (uint32_t)__popc(endv & ((1u << lane) - 1u)), (uint32_t)lane);
       tmem_st_wait();
       __syncwarp();
 
@@ -314,10 +341,6 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       const int fa = lane & 3, fg = lane >> 2;
       float y[2][5][4];
       {
-        const float4* gf = reinterpret_cast<const float4*>(p.gq_frag) + ((size_t)(m * 4 + q) * 8) * 32 + lane;
-        float4 ga[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ga[i] = __ldg(gf + i * 32);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -352,7 +375,6 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       }
 
       // per-caption aggregate over the regions, held by the lane of the caption's last word
-      const bool end_lane = lane == seg_hi && meta.x >= 0;
       float aggacc = agg_identity;
 #pragma unroll
       for (int H = 0; H < 2; ++H) {
@@ -403,20 +425,29 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
           }
         }
         __syncwarp();
-        // ---- 2d. the lane of each caption's last word finishes r_k for the eighteen regions and folds them into its
-        // aggregate: r_k = P_k / max(|v_k| sqrt(Q_k), 1e-8 Z_k) -------------------------------------------------------
+        // ---- 2d. r_k = P_k / max(|v_k| sqrt(Q_k), 1e-8 Z_k) for every (caption end, region) pair, one pair per lane and
+        // round; the value (already exponentiated for LSE) replaces P_k in the end row, whose lane then folds the eighteen
+        // of them into its aggregate -----------------------------------------------------------------------------------
+        for (int pi = lane; pi < npairs; pi += 32) {
+          const int eo = (pi * 3641) >> 16;                        // pi / 18 for pi < 32 * 18
+          const int k = pi - 18 * eo;
+          const uint32_t rowoff = lds_u8(endlist + (uint32_t)eo) * ROW_BYTES + 4u * (uint32_t)k;
+          const float P = lds_f1(wk + rowoff), Q = lds_f1(wk + rowoff + 72), Z = lds_f1(es + rowoff + (uint32_t)(72 * H));
+          const float vn = __ldg(p.vnorm + (size_t)img * R + 18 * H + k);
+          const float r = __fdividef(P, fmaxf(vn * sqrt_approx(fmaxf(Q, 0.f)), 1e-8f * Z));
+          sts_f1(wk + rowoff, p.agg == ITR_AGG_LSE ? ex2f(r * p.c_lse) : r);
+        }
+        __syncwarp();
         if (end_lane) {
-          const uint32_t tw = wk + (uint32_t)lane * ROW_BYTES, te = es + (uint32_t)lane * ROW_BYTES + (uint32_t)(72 * H);
-          const float2* vn2 = reinterpret_cast<const float2*>(p.vnorm + (size_t)img * R + 18 * H);
-#pragma unroll
-          for (int c = 0; c < 9; ++c) {
-            const float2 P2 = lds_f2(tw + 8 * c), Q2 = lds_f2(tw + 72 + 8 * c), Z2 = lds_f2(te + 8 * c);
-            const float2 v2 = __ldg(vn2 + c);
-            const float r0 = __fdividef(P2.x, fmaxf(v2.x * sqrtf(fmaxf(Q2.x, 0.f)), 1e-8f * Z2.x));
-            const float r1 = __fdividef(P2.y, fmaxf(v2.y * sqrtf(fmaxf(Q2.y, 0.f)), 1e-8f * Z2.y));
-            if (p.agg == ITR_AGG_MAX) aggacc = fmaxf(aggacc, fmaxf(r0, r1));
-            else if (p.agg == ITR_AGG_LSE) aggacc += ex2f(r0 * p.c_lse) + ex2f(r1 * p.c_lse);
-            else aggacc += r0 + r1;
+          const uint32_t tw = wk + (uint32_t)lane * ROW_BYTES;
+          const float4 v0 = lds_f4(tw), v1 = lds_f4(tw + 16), v2 = lds_f4(tw + 32), v3 = lds_f4(tw + 48);
+          const float2 v4 = lds_f2(tw + 64);
+          if (p.agg == ITR_AGG_MAX) {
+            aggacc = fmaxf(aggacc, fmaxf(fmaxf(fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w)), fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w))),
+                                         fmaxf(fmaxf(fmaxf(v2.x, v2.y), fmaxf(v2.z, v2.w)), fmaxf(fmaxf(fmaxf(v3.x, v3.y), fmaxf(v3.z, v3.w)), fmaxf(v4.x, v4.y)))));
+          } else {
+            aggacc += (((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w))) +
+                      (((v2.x + v2.y) + (v2.z + v2.w)) + (((v3.x + v3.y) + (v3.z + v3.w)) + (v4.x + v4.y)));
           }
         }
         __syncwarp();
