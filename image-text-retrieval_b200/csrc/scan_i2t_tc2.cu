@@ -12,17 +12,20 @@
 // G_c = W_c W_c^T is the caption's word Gram (fp32 accumulation over the bf16-rounded words, rounded to tf32), handed in
 // the fragment order of the contraction below (caption_gram_frag_kernel).
 //
-// Where t2i reduces over regions (in-thread, TMEM lane = word) and needs one cross-lane sum per region, i2t needs three
-// (Z, P, Q) plus the contraction with G_c.  Per (warp = 32 word rows, image), with two 4.6 KB shared-memory scratches:
-//   1. e (rounded to tf32, the same value everywhere) -> scratch ES (fp32, [row][36]); t = e A is parked in spare
-//      tensor-memory columns;
-//   2. U = G e on the warp's own tensor cores: mma.sync m16n8k8 tf32, A = the quarter's block-diagonal Gram (eight
-//      coalesced 16-byte loads per lane), B = e from ES, 40 MMAs; y = e U at the accumulator positions; then for each half
-//      of the regions (18): rows (t | y) -> scratch WK and 27 lanes walk the 32 rows of WK and, for Z, of ES in place,
-//      restarting at caption ends (the row walk of the t2i kernel) and leave the caption's totals P | Q | Z in its last
-//      row; the lane of that last word finishes r_k for the eighteen regions and folds them into its aggregate -- one
-//      scalar per caption, in a register, is all that survives between the halves;
-//   3. that lane turns the aggregate into the score and stores it.
+// Where t2i reduces over regions (in-thread, TMEM lane = word), i2t needs three sums over a caption's WORDS per region
+// (Z, P, Q) plus the contraction with G_c.  A first version walked shared-memory rows for them and was bound by the
+// shared-memory pipe (1085 wavefronts per warp and item, 93 % busy together with the MMA operand reads); this one moves
+// every contraction onto the warp's own tensor cores (mma.sync m16n8k8 tf32, fp32 accumulation) on TRANSPOSED tiles (rows =
+// regions, columns = words), so that a sum over words is a contraction over the accumulator's column index and chains
+// from registers.  Per (warp = 32 word rows, image), with two 4.6 KB shared-memory scratches:
+//   1. lane = word: e (rounded to tf32, the same value everywhere) -> scratch ES, t = e A -> scratch TS (fp32, [word][36]);
+//   2. U^T = e^T G (A = e^T read from ES in fragment order, B = the quarter's block-diagonal Gram, eight coalesced 16-byte
+//      loads per lane), y^T = e^T o U^T in registers;
+//   3. Z^T = e^T S, Q^T = y^T S, P^T = t^T S with S[word][caption] = [the word belongs to the caption], built from the
+//      end mask in registers; y and t enter split hi + lo, so the sums keep fp32 accuracy;
+//   4. r_k at the accumulator positions (region, caption), aggregated over the regions in-thread and with three shuffles;
+//      the lane of each caption's last word fetches and stores the score.
+// Shared-memory traffic: 72 wavefronts written + 80 read per warp and item.
 // Main loop, barriers and cluster protocol: scan_t2i_tc2.cu (no Gram MMA, no parking: the accumulator is free again as
 // soon as the 32 epilogue warps of the pair have loaded it).
 #include <cuda.h>
@@ -41,24 +44,23 @@ using namespace itr::tc;
 using namespace itr::tc2;
 
 constexpr int STAGES = 3;
-// word-tile pairs per work unit: items differ a lot in cost here (the loop over a caption's words is as long as the
-// longest caption of the warp) and an evaluation fold is small, so units are kept short for the static schedule's balance
-constexpr int I2T_BAND = 32;
+// word-tile pairs per work unit: an evaluation fold is small (206 pairs x 250 image tiles over 74 CTA pairs), so units are
+// kept short for the static schedule's balance (measured: 8 -> 7.83 ms, 32 -> 8.08 ms, 64 -> 8.18 ms on one fold)
+constexpr int I2T_BAND = 8;
 constexpr int AUX_BYTES = BLOCK_M * 16;            // row metadata of the CTA's word tile
 constexpr int ROW_BYTES = 36 * 4;                  // one scratch row: 36 floats
 constexpr int WARP_SCRATCH = 32 * ROW_BYTES;       // 4608
 constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_ES = SMEM_AUX + 2 * AUX_BYTES;
-constexpr int SMEM_WK = SMEM_ES + NUM_EPI_WARPS * WARP_SCRATCH;
-constexpr int SMEM_LIST = SMEM_WK + NUM_EPI_WARPS * WARP_SCRATCH;       // per warp: rows of its caption ends, 32 bytes
-constexpr int SMEM_BARS = SMEM_LIST + NUM_EPI_WARPS * 32;
+constexpr int SMEM_TS = SMEM_ES + NUM_EPI_WARPS * WARP_SCRATCH;
+constexpr int SMEM_BARS = SMEM_TS + NUM_EPI_WARPS * WARP_SCRATCH + 64;      // + slack: fragment reads of padding rows run 48 bytes past a scratch
 constexpr int NUM_BARS = 2 * STAGES + 8;
 constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
-static_assert(SMEM_AUX % 16 == 0 && SMEM_ES % 16 == 0 && SMEM_WK % 16 == 0 && SMEM_BARS % 8 == 0, "alignment");
+static_assert(SMEM_AUX % 16 == 0 && SMEM_ES % 16 == 0 && SMEM_TS % 16 == 0 && SMEM_BARS % 8 == 0, "alignment");
 
 struct Params {
   const int4* row_meta;        // [n_wt*128]
@@ -68,6 +70,8 @@ struct Params {
   int agg;
   float c_sm, c_lse, inv_lse;
   float* scores; long long ld;
+  int band;
+  int skip_epilogue;           // experiments: main loop only
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -96,11 +100,14 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// Round-to-nearest (ties away in magnitude) to tf32's 10-bit mantissa with two integer instructions; cvt.rna.tf32.f32
+// expands to a NaN/Inf-aware sequence of ~6.  The values seen here are finite.
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// hi part of a hi + lo split: the tensor core ignores the low 13 bits of a tf32 operand, so plain truncation is the hi
+// the hardware would see anyway; lo = x - hi is exact in fp32
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // D (16x8, f32) += A (16x8, row) * B (8x8, col), tf32 operands held as f32 bit patterns
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, float b0, float b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -168,12 +175,12 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
 
   using Schedule = ScheduleT<false>;
   using ItemIter = ItemIterT<false>;
-  const Schedule sched(p.n_wp, p.n_it, nullptr, 0, I2T_BAND);
+  const Schedule sched(p.n_wp, p.n_it, nullptr, 0, p.band);
   const int first = (int)(blockIdx.x >> 1);
   const int step = (int)(gridDim.x >> 1);
 
   if (warp < EPI_WARP0) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ==============================
     int stage = 0; uint32_t phase = 0;
@@ -250,9 +257,8 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t es = sbase + SMEM_ES + (uint32_t)(warp - EPI_WARP0) * WARP_SCRATCH;
-    const uint32_t wk = sbase + SMEM_WK + (uint32_t)(warp - EPI_WARP0) * WARP_SCRATCH;
-    const uint32_t endlist = sbase + SMEM_LIST + (uint32_t)(warp - EPI_WARP0) * 32;
-    const uint32_t tpark = tmem_base + 2 * ACC_PITCH + 56 * g + lane_sel;      // 36 of the group's 56 spare TMEM columns
+    const uint32_t ts = sbase + SMEM_TS + (uint32_t)(warp - EPI_WARP0) * WARP_SCRATCH;
+    const int fa = lane & 3, fg = lane >> 2;                                   // mma.sync fragment coordinates
     const float shift = -fabsf(p.c_sm);
     const float agg_identity = (p.agg == ITR_AGG_MAX) ? -INFINITY : 0.f;
 
@@ -265,7 +271,7 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       mbar_wait_sleep(afull_bar(b), (it >> 1) & 1);
       int4 meta = make_int4(-1, 0, lane | (lane << 8), 0);
       if (word_ok) meta = lds_i4(sbase + SMEM_AUX + b * AUX_BYTES + 16u * (uint32_t)row);
-      const int seg_lo = meta.z & 0xff, seg_hi = (meta.z >> 8) & 0xff;
+      const int seg_hi = (meta.z >> 8) & 0xff;
       // The buffer may be refilled only once every lane HOLDS its metadata: an arrive issued while the loads are still in
       // flight lets the refill overtake them (seen as rare stale rows).  The vote consumes every lane's value, and the
       // arrive depends on its result (lane 31 always ends a caption or is padding, so the mask is never 0).
@@ -273,7 +279,10 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       if (lane == 0 && endmask != 0u) mbar_arrive(aempty_bar(b));
       const bool long_tile = (meta.z >> 16) & 1;
       const int img = n * IMGS + g;
-      const bool valid = img < p.n_img && word_ok && !long_tile;      // warp-uniform
+      const bool end_lane = lane == seg_hi && meta.x >= 0;
+      const uint32_t endv = __ballot_sync(0xffffffffu, end_lane);                   // last words of the real captions
+      const uint32_t realv = __ballot_sync(0xffffffffu, meta.x >= 0);              // real (non-padding) word rows
+      const bool valid = img < p.n_img && word_ok && !long_tile && endv != 0u;      // warp-uniform
 
       const uint32_t tacc = tmem_base + b * ACC_PITCH + lane_sel;
       mbar_wait_sleep(tfull_bar(b), (it >> 1) & 1);
@@ -285,9 +294,9 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(loaded_bar(b), leader);
-      if (!valid) continue;
+      if (!valid || p.skip_epilogue) continue;
 
-      // ---- 1. per-word l2norm over the regions, softmax numerators e (-> ES), t = e A (-> parked in tensor memory) -----
+      // ---- 1. per-word l2norm over the regions, softmax numerators e (rounded to tf32) and t = e A, lane = word ---------
       float n2 = 0.f;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
@@ -295,169 +304,140 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
         n2 = fmaf(a, a, n2);
       }
       const float cw = __fdividef(p.c_sm, sqrtf(n2) + 1e-8f);
-      const uint32_t myrow = es + (uint32_t)lane * ROW_BYTES;
+      const uint32_t erow = es + (uint32_t)lane * ROW_BYTES, trow = ts + (uint32_t)lane * ROW_BYTES;
 #pragma unroll
       for (int k = 0; k < R; k += 4) {
-        float e[4];
+        float e[4], t[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float raw = A[k + i];
           const float a = CLIPPED ? fmaxf(raw, 0.1f * raw) : raw;
-          e[i] = round_tf32(ex2f(fmaf(a, cw, shift)));      // the tensor-core contraction below reads e as tf32: use the same e everywhere
-          A[k + i] = e[i] * raw;                           // t
+          e[i] = round_tf32(ex2f(fmaf(a, cw, shift)));      // the tensor-core contractions below read e as tf32: the same e everywhere
+          t[i] = e[i] * raw;
         }
-        sts_f4(myrow + 4 * k, e[0], e[1], e[2], e[3]);
+        sts_f4(erow + 4 * k, e[0], e[1], e[2], e[3]);
+        sts_f4(trow + 4 * k, t[0], t[1], t[2], t[3]);
       }
-      {
-        // t leaves the registers: 36 of the group's 56 spare tensor-memory columns (the accumulators end at column 288;
-        // the accumulator itself may be overwritten by the MMA of item t+2 as soon as every warp has loaded it)
-        uint32_t tv[R];
+      // the quarter's Gram in B-fragment order (step 2): b0 = G[8s+2a][8nt+g], b1 = G[8s+2a+1][8nt+g], two n-tiles per float4;
+      // streamed from L1/L2 once per row tile (holding it would cost 32 registers)
+      const float4* gf = reinterpret_cast<const float4*>(p.gq_frag) + ((size_t)(m * 4 + q) * 8) * 32 + lane;
+      const float* vp = p.vnorm + (size_t)img * R + fg;          // |v_k| of this lane's accumulator rows: regions 16 mt + 8 h + g
+      // the Gram is block-diagonal by caption: its 8x8 block (s, nt) is non-zero only if one caption reaches from word group
+      // s into word group nt, i.e. no segment ends between the last word of the lower group and the first of the upper
+      uint32_t gblocks = 0x8421u;                                // the diagonal blocks
 #pragma unroll
-        for (int k = 0; k < R; ++k) tv[k] = __float_as_uint(A[k]);
-        TMEM_ST_X16(tpark, tv, 0);
-        TMEM_ST_X16(tpark + 16, tv, 16);
-        TMEM_ST_X4(tpark + 32, tv, 32);
-      }
-      // the quarter's Gram fragments (step 2a) are requested as soon as t has left the registers
-      float4 ga[8];
-      {
-        const float4* gf = reinterpret_cast<const float4*>(p.gq_frag) + ((size_t)(m * 4 + q) * 8) * 32 + lane;
+      for (int lo = 0; lo < 3; ++lo)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ga[i] = __ldg(gf + i * 32);
-      }
-      // rows of the (real) caption ends, in order: the pairs (caption end, region) of step 2d are dealt to the lanes
-      const bool end_lane = lane == seg_hi && meta.x >= 0;
-      const uint32_t endv = __ballot_sync(0xffffffffu, end_lane);
-      const int npairs = __popc(endv) * 18;
-      if (end_lane) sts_u8(endlist + (uint32_t)__popc(endv & ((1u << lane) - 1u)), (uint32_t)lane);
-      tmem_st_wait();
+        for (int hi = lo + 1; hi < 4; ++hi)
+          if (((endmask >> (8 * lo + 7)) & ((1u << (8 * (hi - lo) - 7)) - 1u)) == 0u) gblocks |= (1u << (4 * lo + hi)) | (1u << (4 * hi + lo));
+      const int my_ord = __popc(endv & ((1u << lane) - 1u));      // meaningful on the lanes that end a caption
+      const int n_ct = (__popc(endv) + 7) >> 3;                  // caption n-tiles of eight: one unless the captions are tiny
       __syncwarp();
 
-      // ---- 2a. U[j][k] = sum over the caption's words j' of G_c[j][j'] e[j'][k] on the warp's own tensor cores: the
-      // quarter's 32x32 block-diagonal Gram (A, pre-arranged in fragment order and tf32-rounded by the Gram kernel) times
-      // e (B, read straight from ES), mma.sync m16n8k8 tf32 -> 2 x 5 accumulator fragments (columns 36..39 are padding).
-      // Within a k-step the contraction index is permuted (logical k = a -> word 8s+2a, k = a+4 -> word 8s+2a+1, the same
-      // in A and B) so that the B reads are free of bank conflicts at the 36-float row pitch.
-      const int fa = lane & 3, fg = lane >> 2;
-      float y[2][5][4];
-      {
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 5; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) y[mt][nt][i] = 0.f;
-        const uint32_t bbase = es + (uint32_t)(2 * fa) * ROW_BYTES + 4u * (uint32_t)fg;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          float b0[5], b1[5];
-#pragma unroll
-          for (int nt = 0; nt < 5; ++nt) {
-            b0[nt] = lds_f1(bbase + (uint32_t)(8 * s * ROW_BYTES + 32 * nt));
-            b1[nt] = lds_f1(bbase + (uint32_t)((8 * s + 1) * ROW_BYTES + 32 * nt));
-          }
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) mma_tf32(y[mt][nt], ga[mt * 4 + s], b0[nt], b1[nt]);
-        }
-        // y = e U at the accumulator positions: rows 16 mt + 8 h + fg, columns 8 nt + 2 fa (+1)
-        const uint32_t ebase = es + (uint32_t)fg * ROW_BYTES + 8u * (uint32_t)fa;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
-              const float2 e2 = lds_f2(ebase + (uint32_t)((16 * mt + 8 * h) * ROW_BYTES + 32 * nt));
-              y[mt][nt][2 * h] *= e2.x; y[mt][nt][2 * h + 1] *= e2.y;
-            }
-      }
-
-      // per-caption aggregate over the regions, held by the lane of the caption's last word
-      float aggacc = agg_identity;
-#pragma unroll
-      for (int H = 0; H < 2; ++H) {
-        // ---- 2b. walk scratch rows for eighteen regions: [t | y]; e is walked in place in ES -----------------------------
-        {
-          float t[18];
-          TMEM_LD_X16(tpark + 18 * H, t, 0);
-          TMEM_LD_X2(tpark + 18 * H + 16, t, 16);
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int nt = 2 * H; nt < 2 * H + 3; ++nt) {
-                const int rel = 8 * nt + 2 * fa - 18 * H;           // column pair within the half (even)
-                if (rel >= 0 && rel < 18)
-                  sts_f2(wk + (uint32_t)((16 * mt + 8 * h + fg) * ROW_BYTES + 72 + 4 * rel), y[mt][nt][2 * h], y[mt][nt][2 * h + 1]);
-              }
-          tmem_ld_wait();
-          const uint32_t dst = wk + (uint32_t)lane * ROW_BYTES;
-          sts_f4(dst, t[0], t[1], t[2], t[3]);
-          sts_f4(dst + 16, t[4], t[5], t[6], t[7]);
-          sts_f4(dst + 32, t[8], t[9], t[10], t[11]);
-          sts_f4(dst + 48, t[12], t[13], t[14], t[15]);
-          sts_f2(dst + 64, t[16], t[17]);
-        }
-        __syncwarp();
-        // ---- 2c. row walk (as in the t2i kernel): 27 lanes, two columns each (18 on the scratch: P and Q, 9 on ES: Z),
-        // restart at every caption end and leave the caption's totals in its last row -------------------------------------
-        if (lane < 27) {
-          const uint32_t col = lane < 18 ? wk + 8u * (uint32_t)lane : es + (uint32_t)(72 * H) + 8u * (uint32_t)(lane - 18);
-          float2 acc = make_float2(0.f, 0.f);
+      // Everything below works on TRANSPOSED tiles (rows = regions, padded 36 -> 48 = three m16 tiles; columns = the 32
+      // words), mma.sync m16n8k8 tf32 with fp32 accumulation, so that sums over a caption's words are contractions over
+      // the accumulator's COLUMN index and chain from registers.  Contraction index of k-step s: logical k = a -> word
+      // 8s+2a, k = a+4 -> word 8s+2a+1 (the same permutation in every operand): with it the A fragment of k-step s sits at
+      // exactly the accumulator positions of word n-tile s, and the fragment reads are free of bank conflicts at the
+      // 36-float row pitch.
+      //   2. U^T = e^T G            A = e^T from ES, B = the quarter's block-diagonal Gram (registers)
+      //      y^T = e^T o U^T        element-wise, in registers
+      //   3. Z^T = e^T S, Q^T = y^T S, P^T = t^T S     S[word][caption] = 1 if the word belongs to the caption (built from
+      //      the end mask in registers); y and t are split hi + lo so that the sums keep fp32 accuracy
+      //   4. r = P / max(|v| sqrt(Q), 1e-8 Z) at the accumulator positions (region, caption); aggregate over the regions:
+      //      in-thread over the row tiles, three shuffles over g; the lane that ends the caption fetches and stores it.
 #pragma unroll 1
-          for (int j0 = 0; j0 < 32; j0 += 8) {
-            float2 v[8];
-            const uint32_t blk = col + (uint32_t)(j0 * ROW_BYTES);
-            const uint32_t ends = endmask >> j0;
+      for (int ct = 0; ct < n_ct; ++ct) {
+        float sb[4][2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = lds_f2(blk + (uint32_t)(j * ROW_BYTES));
+        for (int s = 0; s < 4; ++s)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc.x += v[j].x; acc.y += v[j].y;
-              if ((ends >> j) & 1u) {
-                sts_f2(blk + (uint32_t)(j * ROW_BYTES), acc.x, acc.y);
-                acc = make_float2(0.f, 0.f);
-              }
+          for (int o = 0; o < 2; ++o) {
+            // caption ordinal (within the quarter) of word 8 s + 2 a + o; padding rows belong to no caption
+            const int w = 8 * s + 2 * fa + o;
+            const bool mine = ((realv >> w) & 1u) && __popc(endv & ((1u << w) - 1u)) == 8 * ct + fg;
+            sb[s][o] = mine ? 1.f : 0.f;
+          }
+        float agg[2] = {agg_identity, agg_identity};             // captions 8 ct + 2 a (+1), this lane's regions
+#pragma unroll 1
+        for (int mt = 0; mt < 3; ++mt) {
+          // A fragments of e^T: a0 = e[8s+2a][16mt+g], a1 = e[8s+2a][16mt+g+8], a2, a3 = the same of word 8s+2a+1; rows 36..47 are
+          // padding (a1 = a3 = 0 in the last tile; its a0/a2 of g >= 4 read finite neighbours and feed rows nobody uses)
+          const uint32_t fo = (uint32_t)(2 * fa) * ROW_BYTES + 4u * (uint32_t)(16 * mt + fg);
+          float4 ea[4];
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint32_t ad = es + fo + (uint32_t)(8 * s * ROW_BYTES);
+            ea[s].x = lds_f1(ad); ea[s].z = lds_f1(ad + ROW_BYTES);
+            ea[s].y = mt < 2 ? lds_f1(ad + 32) : 0.f; ea[s].w = mt < 2 ? lds_f1(ad + ROW_BYTES + 32) : 0.f;
+          }
+          float u[4][4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[nt][i] = 0.f;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const float4 g01 = __ldg(gf + (2 * s) * 32), g23 = __ldg(gf + (2 * s + 1) * 32);
+            if (gblocks & (1u << (4 * s + 0))) mma_tf32(u[0], ea[s], g01.x, g01.y);
+            if (gblocks & (1u << (4 * s + 1))) mma_tf32(u[1], ea[s], g01.z, g01.w);
+            if (gblocks & (1u << (4 * s + 2))) mma_tf32(u[2], ea[s], g23.x, g23.y);
+            if (gblocks & (1u << (4 * s + 3))) mma_tf32(u[3], ea[s], g23.z, g23.w);
+          }
+          // hi and lo parts accumulate separately: independent chains of four MMAs instead of one of eight
+          float zq[4] = {0.f, 0.f, 0.f, 0.f}, qq[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+          float ql[4] = {0.f, 0.f, 0.f, 0.f}, pl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            mma_tf32(zq, ea[s], sb[s][0], sb[s][1]);
+            // y^T at the accumulator positions of word tile s, re-ordered into an A fragment: (c0, c2, c1, c3)
+            float4 y = make_float4(u[s][0] * ea[s].x, u[s][2] * ea[s].y, u[s][1] * ea[s].z, u[s][3] * ea[s].w);
+            float4 yh = make_float4(trunc_tf32(y.x), trunc_tf32(y.y), trunc_tf32(y.z), trunc_tf32(y.w));
+            mma_tf32(qq, yh, sb[s][0], sb[s][1]);
+            mma_tf32(ql, make_float4(y.x - yh.x, y.y - yh.y, y.z - yh.z, y.w - yh.w), sb[s][0], sb[s][1]);
+          }
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint32_t ad = ts + fo + (uint32_t)(8 * s * ROW_BYTES);
+            float4 t4;
+            t4.x = lds_f1(ad); t4.z = lds_f1(ad + ROW_BYTES);
+            t4.y = mt < 2 ? lds_f1(ad + 32) : 0.f; t4.w = mt < 2 ? lds_f1(ad + ROW_BYTES + 32) : 0.f;
+            float4 th = make_float4(trunc_tf32(t4.x), trunc_tf32(t4.y), trunc_tf32(t4.z), trunc_tf32(t4.w));
+            mma_tf32(pq, th, sb[s][0], sb[s][1]);
+            mma_tf32(pl, make_float4(t4.x - th.x, t4.y - th.y, t4.z - th.z, t4.w - th.w), sb[s][0], sb[s][1]);
+          }
+          // accumulator positions: [2h + cc] = (region 16 mt + 8 h + g, caption 8 ct + 2 a + cc)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const bool region_ok = 16 * mt + 8 * h + fg < R;                  // regions 36..47: padding
+            const float vk = region_ok ? __ldg(vp + 16 * mt + 8 * h) : 1.f;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const float P = pq[2 * h + cc] + pl[2 * h + cc], Q = qq[2 * h + cc] + ql[2 * h + cc], Z = zq[2 * h + cc];
+              const float r = __fdividef(P, fmaxf(vk * sqrt_approx(fmaxf(Q, 0.f)), 1e-8f * Z));
+              const float val = p.agg == ITR_AGG_LSE ? ex2f(r * p.c_lse) : r;
+              if (p.agg == ITR_AGG_MAX) agg[cc] = region_ok ? fmaxf(agg[cc], val) : agg[cc];
+              else agg[cc] += region_ok ? val : 0.f;
             }
           }
         }
-        __syncwarp();
-        // ---- 2d. r_k = P_k / max(|v_k| sqrt(Q_k), 1e-8 Z_k) for every (caption end, region) pair, one pair per lane and
-        // round; the value (already exponentiated for LSE) replaces P_k in the end row, whose lane then folds the eighteen
-        // of them into its aggregate -----------------------------------------------------------------------------------
-        for (int pi = lane; pi < npairs; pi += 32) {
-          const int eo = (pi * 3641) >> 16;                        // pi / 18 for pi < 32 * 18
-          const int k = pi - 18 * eo;
-          const uint32_t rowoff = lds_u8(endlist + (uint32_t)eo) * ROW_BYTES + 4u * (uint32_t)k;
-          const float P = lds_f1(wk + rowoff), Q = lds_f1(wk + rowoff + 72), Z = lds_f1(es + rowoff + (uint32_t)(72 * H));
-          const float vn = __ldg(p.vnorm + (size_t)img * R + 18 * H + k);
-          const float r = __fdividef(P, fmaxf(vn * sqrt_approx(fmaxf(Q, 0.f)), 1e-8f * Z));
-          sts_f1(wk + rowoff, p.agg == ITR_AGG_LSE ? ex2f(r * p.c_lse) : r);
-        }
-        __syncwarp();
-        if (end_lane) {
-          const uint32_t tw = wk + (uint32_t)lane * ROW_BYTES;
-          const float4 v0 = lds_f4(tw), v1 = lds_f4(tw + 16), v2 = lds_f4(tw + 32), v3 = lds_f4(tw + 48);
-          const float2 v4 = lds_f2(tw + 64);
-          if (p.agg == ITR_AGG_MAX) {
-            aggacc = fmaxf(aggacc, fmaxf(fmaxf(fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w)), fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w))),
-                                         fmaxf(fmaxf(fmaxf(v2.x, v2.y), fmaxf(v2.z, v2.w)), fmaxf(fmaxf(fmaxf(v3.x, v3.y), fmaxf(v3.z, v3.w)), fmaxf(v4.x, v4.y)))));
-          } else {
-            aggacc += (((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w))) +
-                      (((v2.x + v2.y) + (v2.z + v2.w)) + (((v3.x + v3.y) + (v3.z + v3.w)) + (v4.x + v4.y)));
+        // over the regions held by the other seven g of the same a
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int sh = 4; sh < 32; sh <<= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, agg[cc], sh);
+            agg[cc] = p.agg == ITR_AGG_MAX ? fmaxf(agg[cc], o) : agg[cc] + o;
           }
+        // ---- 5. the lane of each caption's last word fetches its caption's aggregate (lane a = (ordinal % 8) / 2) and stores it
+        const int src = (my_ord & 7) >> 1;
+        const float v0 = __shfl_sync(0xffffffffu, agg[0], src), v1 = __shfl_sync(0xffffffffu, agg[1], src);
+        if (end_lane && (my_ord >> 3) == ct) {
+          float tot = (my_ord & 1) ? v1 : v0;
+          if (p.agg == ITR_AGG_LSE) tot = lg2f(tot) * p.inv_lse;
+          if (p.agg == ITR_AGG_MEAN) tot = tot * (1.0f / (float)R);
+          p.scores[(size_t)img * p.ld + meta.x] = tot;
         }
-        __syncwarp();
-      }
-      // ---- 3. ... and stores the score --------------------------------------------------------------------------------
-      if (end_lane) {
-        float tot = aggacc;
-        if (p.agg == ITR_AGG_LSE) tot = lg2f(tot) * p.inv_lse;
-        if (p.agg == ITR_AGG_MEAN) tot = tot * (1.0f / (float)R);
-        p.scores[(size_t)img * p.ld + meta.x] = tot;
       }
       __syncwarp();
     }
@@ -472,11 +452,11 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
   }
 }
 
-// Word Gram of every packed word tile in the order the fused kernel's mma.sync A operand wants it.  Per 32-row quarter the
-// Gram is block-diagonal (G[j][j'] = w_j . w_j' for two words of the same caption, else 0); out[tile][quarter][mt][s][lane]
-// is the float4 (a0..a3) of the m16n8k8 fragment of rows 16 mt .. +15 and k-step s, with the kernel's permutation of the
-// contraction index: a0 = G[16mt+g][8s+2a], a1 = G[16mt+g+8][8s+2a], a2 = G[16mt+g][8s+2a+1], a3 = G[16mt+g+8][8s+2a+1]
-// (g = lane / 4, a = lane % 4), rounded to tf32.  One warp per word row; the row stays in registers (bf16 pairs).
+// Word Gram of every packed word tile in the order the fused kernel's mma.sync B operand wants it.  Per 32-row quarter the
+// Gram is block-diagonal (G[j][j'] = w_j . w_j' for two words of the same caption, else 0) and symmetric;
+// out[tile][quarter][s][p][lane] is the float4 (b0, b1 of word n-tile 2p, b0, b1 of n-tile 2p+1) of k-step s with the kernel's
+// permutation of the contraction index: b0 = G[8s+2a][8nt+g], b1 = G[8s+2a+1][8nt+g] (g = lane / 4, a = lane % 4), rounded
+// to tf32.  One warp per word row; the row stays in registers (bf16 pairs).
 __global__ void __launch_bounds__(256)
 caption_gram_frag_kernel(const uint16_t* __restrict__ words, const int4* __restrict__ row_meta, int n_tiles, float* __restrict__ out) {
   const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -511,8 +491,8 @@ caption_gram_frag_kernel(const uint16_t* __restrict__ words, const int4* __restr
       s = warp_sum(s);
       if (lane == 0) {
         const int jp = seg_lo + dlt;                                           // quarter-local index of the partner word
-        const int mt = jl >> 4, g = jl & 7, hrow = (jl >> 3) & 1, ks = jp >> 3, a = (jp & 7) >> 1, odd = jp & 1;
-        tile_out[((((q * 2 + mt) * 4 + ks) * 32) + 4 * g + a) * 4 + hrow + 2 * odd] = round_tf32(s);
+        const int ks = jp >> 3, a = (jp & 7) >> 1, odd = jp & 1, nt = jl >> 3, g = jl & 7;
+        tile_out[((((q * 4 + ks) * 2 + (nt >> 1)) * 32) + 4 * g + a) * 4 + 2 * (nt & 1) + odd] = round_tf32(s);
       }
     }
   }
@@ -536,7 +516,7 @@ static int launch(const CUtensorMap& map_w, const CUtensorMap& map_i, const Para
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2; }
     max_pairs = n < sms / 2 ? n : sms / 2;
   }
-  const long long units = (long long)((p.n_wp + I2T_BAND - 1) / I2T_BAND) * p.n_it;
+  const long long units = (long long)((p.n_wp + p.band - 1) / p.band) * p.n_it;
   if (units <= 0) return ITR_OK;
   const int pairs = (int)(units < max_pairs ? units : max_pairs);
   kern<<<2 * pairs, NUM_THREADS, SMEM_ALLOC, stream>>>(map_w, map_i, p);
@@ -590,6 +570,8 @@ extern "C" int itr_scan_i2t_scores_bf16(const uint16_t* images_bf16, const float
   p.c_lse = lambda_lse * 1.4426950408889634f;
   p.inv_lse = 0.6931471805599453f / lambda_lse;
   p.scores = scores; p.ld = ld_scores;
+  p.band = getenv("ITR_B200_I2T_BAND") ? atoi(getenv("ITR_B200_I2T_BAND")) : tc2i::I2T_BAND;
+  p.skip_epilogue = getenv("ITR_B200_I2T_SKIP") != nullptr;
   if ((long long)p.n_wp * p.n_it >= (1ll << 31))
     return fail(ITR_ERR_INVALID, "itr_scan_i2t_scores_bf16: %lld tile pairs exceed the 2^31 scheduler range; split the call", (long long)p.n_wp * p.n_it);
   cudaStream_t st = as_stream(stream);
