@@ -71,7 +71,6 @@ struct Params {
   float c_sm, c_lse, inv_lse;
   float* scores; long long ld;
   int band;
-  int skip_epilogue;           // experiments: main loop only
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -294,7 +293,7 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(loaded_bar(b), leader);
-      if (!valid || p.skip_epilogue) continue;
+      if (!valid) continue;
 
       // ---- 1. per-word l2norm over the regions, softmax numerators e (rounded to tf32) and t = e A, lane = word ---------
       float n2 = 0.f;
@@ -570,8 +569,7 @@ extern "C" int itr_scan_i2t_scores_bf16(const uint16_t* images_bf16, const float
   p.c_lse = lambda_lse * 1.4426950408889634f;
   p.inv_lse = 0.6931471805599453f / lambda_lse;
   p.scores = scores; p.ld = ld_scores;
-  p.band = getenv("ITR_B200_I2T_BAND") ? atoi(getenv("ITR_B200_I2T_BAND")) : tc2i::I2T_BAND;
-  p.skip_epilogue = getenv("ITR_B200_I2T_SKIP") != nullptr;
+  p.band = tc2i::I2T_BAND;
   if ((long long)p.n_wp * p.n_it >= (1ll << 31))
     return fail(ITR_ERR_INVALID, "itr_scan_i2t_scores_bf16: %lld tile pairs exceed the 2^31 scheduler range; split the call", (long long)p.n_wp * p.n_it);
   cudaStream_t st = as_stream(stream);
