@@ -521,10 +521,14 @@ caption_gram_kernel(const uint16_t* __restrict__ words, const int32_t* __restric
   const int c = blockIdx.x, n = cap_lens[c], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint16_t* W = words + (size_t)cap_row0[c] * d;
   float* g = gram + gram_off[c];
-  for (int o = warp; o < n * (n + 1) / 2; o += 4) {
-    int j = 0, rem = o;
-    while (rem > j) { rem -= j + 1; ++j; }
-    const int j2 = rem;
+  // blockIdx.y splits the caption's n (n + 1) / 2 word pairs: a handful of long captions would otherwise keep a handful
+  // of blocks busy for a millisecond (measured: 6 captions of up to 72 words, 0.78 ms with one block per caption)
+  for (int o = warp + 4 * blockIdx.y; o < n * (n + 1) / 2; o += 4 * gridDim.y) {
+    // pair o -> (j, j2 <= j): j = floor((sqrt(8 o + 1) - 1) / 2), corrected for rounding
+    int j = (int)((sqrtf(8.f * (float)o + 1.f) - 1.f) * 0.5f);
+    while (j * (j + 1) / 2 > o) --j;
+    while ((j + 1) * (j + 2) / 2 <= o) ++j;
+    const int j2 = o - j * (j + 1) / 2;
     const uint32_t* a = reinterpret_cast<const uint32_t*>(W + (size_t)j * d);
     const uint32_t* b = reinterpret_cast<const uint32_t*>(W + (size_t)j2 * d);
     float s = 0.f;
@@ -948,7 +952,10 @@ extern "C" int itr_scan_caption_gram_f32(const uint16_t* words_bf16, const int32
   ITR_REQUIRE(words_bf16 && cap_row0 && cap_lens && gram_off && gram, "itr_scan_caption_gram_f32: null pointer");
   ITR_REQUIRE(d > 0 && d % 2 == 0, "itr_scan_caption_gram_f32: embed size must be even");
   if (n_cap <= 0) return ITR_OK;
-  caption_gram_kernel<<<n_cap, 128, 0, as_stream(stream)>>>(words_bf16, cap_row0, cap_lens, gram_off, d, gram);
+  // about four blocks per SM in total: many captions -> one block each, few captions -> their pairs spread over blocks
+  int split = (4 * 148 + n_cap - 1) / n_cap;
+  split = split < 1 ? 1 : (split > 64 ? 64 : split);
+  caption_gram_kernel<<<dim3((unsigned)n_cap, (unsigned)split), 128, 0, as_stream(stream)>>>(words_bf16, cap_row0, cap_lens, gram_off, d, gram);
   ITR_CHECK_LAUNCH();
   return ITR_OK;
 }
