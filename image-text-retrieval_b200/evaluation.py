@@ -196,7 +196,7 @@ def _tc_t2i_inputs(model, img_embs, cap_embs, ln, image_group, dev):
     if image_group is not None:
         pi = ops.prepare_images_sharded(img_embs, image_group, dev)
     else:
-        pi = ops.prepare_images(_to_device(img_embs, dev))
+        pi = ops.prepare_images_streamed(img_embs, dev)      # large host arrays: uploaded in chunks, scored as they land
     return pi, caps, norm
 
 

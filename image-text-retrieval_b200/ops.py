@@ -252,25 +252,48 @@ class PreparedImages:
     # are being pulled over NVLink by the copy engines and are valid once `gathered` has been waited for
     local_rows: tuple = None
     gathered: object = None       # torch.cuda.Event recorded on the gather stream
+    # host images uploaded in chunks (prepare_images_streamed): [(lo, hi, event)], rows [lo, hi) are valid once the event
+    # (recorded on the upload stream after the chunk's cast / Gram kernel) has been waited for
+    pending: list = None
 
     def rows(self, lo, hi):
         """The images [lo, hi) as a PreparedImages of their own (views)."""
         return PreparedImages(self.images_bf16[lo:hi], self.gram_pack[lo:hi], hi - lo)
 
     def wait_gathered(self):
-        """Make the current stream wait until every rank's rows have arrived (no-op on one GPU)."""
+        """Make the current stream wait until every row is valid: the other ranks' rows have arrived, every uploaded chunk
+        is prepared (no-op for images prepared on the current stream)."""
+        stream = torch.cuda.current_stream(self.images_bf16.device)
         if self.gathered is not None:
-            torch.cuda.current_stream(self.images_bf16.device).wait_event(self.gathered)
+            stream.wait_event(self.gathered)
             self.gathered = None
+        if self.pending:
+            for _, _, ev in self.pending:
+                stream.wait_event(ev)
+        self.pending = None
 
     def row_ranges(self):
-        """[(lo, hi, needs_gather)] in the order the rows become valid: this rank's own rows first."""
+        """[(lo, hi, token)] in the order the rows become valid (this rank's own rows first, uploaded chunks in upload
+        order); pass the token to wait_rows() before launching on the range."""
+        if self.pending:
+            return list(self.pending)
         if self.gathered is None or self.local_rows is None:
             return [(0, self.n_img, self.gathered is not None)]
         lo, hi = self.local_rows
         out = [(lo, hi, False)] if hi > lo else []
         out += [(a, b, True) for a, b in ((0, lo), (hi, self.n_img)) if b > a]
         return out
+
+    def wait_rows(self, token):
+        """Make the current stream wait for the rows a row_ranges() entry stands for."""
+        if token is True:
+            self.wait_gathered()
+        elif token is not None and token is not False:
+            torch.cuda.current_stream(self.images_bf16.device).wait_event(token)
+
+    def ranges_consumed(self):
+        """Every entry of row_ranges() has been waited for on the current stream: from now on all rows are valid there."""
+        self.pending = None
 
 
 @dataclass
@@ -371,6 +394,56 @@ def prepare_images(images, out=None, gram=None) -> PreparedImages:
         check(capi.lib().itr_scan_prep_images_bf16(ptr(images), n_img, images.size(1), images.size(2), ptr(out), ptr(gram),
                                                    stream_ptr()))
     return PreparedImages(out, gram, n_img)
+
+
+STREAMED_IMAGES_MIN_BYTES = 128 << 20
+STREAMED_IMAGE_CHUNKS = 8
+_UPLOAD_STREAMS = {}
+
+
+def _upload_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _UPLOAD_STREAMS:
+        _UPLOAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _UPLOAD_STREAMS[key]
+
+
+def prepare_images_streamed(images, device, chunks=None) -> PreparedImages:
+    """prepare_images for a large HOST image array (pinned or pageable float32): the array is uploaded in `chunks` row
+    ranges on an upload stream, each range cast / Grammed as soon as it has landed, and the result's row_ranges() hand the
+    ranges out in upload order with the event to wait for -- the score kernels start on the first range while the others
+    are still on the PCIe bus (at COCO-5K size the 737 MB of images are 14 ms of transfer nothing else could hide).
+    Small arrays, and arrays already on the device, take prepare_images directly."""
+    dev = torch.device(device)
+    t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+    if t.dtype != torch.float32:
+        t = t.float()
+    nbytes = t.numel() * 4
+    if t.is_cuda or nbytes < STREAMED_IMAGES_MIN_BYTES or t.dim() != 3:
+        if not t.is_cuda and not t.is_pinned() and nbytes >= STAGED_UPLOAD_MIN_BYTES:
+            return prepare_images(upload_pageable(t.contiguous(), dev))
+        return prepare_images(t.to(dev, non_blocking=True))
+    t = t.contiguous()
+    n_img = t.size(0)
+    k = int(chunks or STREAMED_IMAGE_CHUNKS)
+    per = max(capi.TILE_IMAGES, -(-n_img // k) // capi.TILE_IMAGES * capi.TILE_IMAGES)       # whole image tiles per range
+    per += capi.TILE_IMAGES if per * k < n_img else 0
+    img_all = torch.empty(n_img, capi.REGIONS, capi.EMBED, device=dev, dtype=torch.bfloat16)
+    gram_all = torch.empty(n_img, capi.GRAM_BYTES, device=dev, dtype=torch.uint8)
+    main, up = torch.cuda.current_stream(dev), _upload_stream(dev)
+    up.wait_stream(main)
+    pending = []
+    with torch.cuda.stream(up):
+        for lo in range(0, n_img, per):
+            hi = min(lo + per, n_img)
+            stage = t[lo:hi].to(dev, non_blocking=True) if t.is_pinned() else upload_pageable(t[lo:hi], dev)
+            prepare_images(stage, out=img_all[lo:hi], gram=gram_all[lo:hi])
+            ev = torch.cuda.Event()
+            ev.record(up)
+            pending.append((lo, hi, ev))
+    for x in (img_all, gram_all):
+        x.record_stream(up)
+    return PreparedImages(img_all, gram_all, n_img, pending=pending)
 
 
 _SYM = {}              # (group name, device) -> symmetric-memory workspace of the image gather
@@ -541,14 +614,14 @@ def scan_t2i_scores_bf16(pi: PreparedImages, pc: PreparedCaptions, raw_feature_n
     assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
     with torch.cuda.device(dev):
         # multi-GPU: this rank's own image rows first, the others once the copy engines have delivered them
-        for lo, hi, needs_gather in pi.row_ranges():
-            if needs_gather:
-                pi.wait_gathered()
+        for lo, hi, token in pi.row_ranges():
+            pi.wait_rows(token)
             o = out[lo:hi]
             check(capi.lib().itr_scan_t2i_scores_bf16(ptr(pi.images_bf16[lo:hi]), ptr(pi.gram_pack[lo:hi]), hi - lo,
                                                       ptr(pc.words_bf16), ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles, norm,
                                                       agg, float(lambda_softmax), float(lambda_lse), ptr(o),
                                                       out.stride(0) if out.numel() else max(pc.n_cap, 1), stream_ptr()))
+        pi.ranges_consumed()
     return out
 
 
@@ -587,9 +660,8 @@ def scan_t2i_count(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, a
     if out is not None:
         assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (pi.n_img, pc.n_cap)
     with torch.cuda.device(dev):
-        for k, (lo, hi, needs_gather) in enumerate(pi.row_ranges()):
-            if needs_gather:
-                pi.wait_gathered()
+        for k, (lo, hi, token) in enumerate(pi.row_ranges()):
+            pi.wait_rows(token)
             o = out[lo:hi] if out is not None else None
             check(capi.lib().itr_scan_t2i_count_bf16(ptr(pi.images_bf16[lo:hi]), ptr(pi.gram_pack[lo:hi]), hi - lo,
                                                      ptr(pc.words_bf16), ptr(pc.row_meta), ptr(pc.row_wnorm), pc.n_tiles,
@@ -597,6 +669,7 @@ def scan_t2i_count(pi: PreparedImages, pc: PreparedCaptions, raw_feature_norm, a
                                                      int(cap_offset), ptr(thr_col), ptr(thr_row[lo:hi]), ptr(o),
                                                      out.stride(0) if out is not None else 0, ptr(cnt_row[lo:hi]), ptr(cnt_col),
                                                      ptr(best_row[lo:hi]), ptr(best_col), int(lo), int(k > 0), stream_ptr()))
+        pi.ranges_consumed()
     return cnt_row, cnt_col, best_row, best_col
 
 
@@ -628,16 +701,22 @@ def scan_t2i_scores_from_host(pi: PreparedImages, captions, cap_lens, raw_featur
     ln = lengths_to_numpy(cap_lens, n_cap)
     dev = pi.images_bf16.device
     out = torch.empty(pi.n_img, n_cap, device=dev, dtype=torch.float32)
+    # images still arriving in chunks (prepare_images_streamed): the first caption chunk is scored range by range as they
+    # land, so it is made large enough to keep the SMs busy for the whole upload, and the later caption chunks leave the
+    # PCIe bus to the images until those are all in
+    images_landed = pi.pending[-1][2] if pi.pending else None
     if chunks is None:
-        chunks = host_caption_chunks(ln)
+        chunks = host_caption_chunks(ln, fractions=(3.0 / 16, 5.0 / 16, 1.0 / 2)) if images_landed is not None else host_caption_chunks(ln)
     if len(chunks) == 1:
         pc = prepare_captions(captions, ln, device=dev)
         return scan_t2i_scores_bf16(pi, pc, raw_feature_norm, agg_func, lambda_softmax, lambda_lse, out=out)
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     side.wait_stream(main)
-    for c0, c1 in chunks:
+    for k, (c0, c1) in enumerate(chunks):
         with torch.cuda.stream(side):
+            if k > 0 and images_landed is not None:
+                side.wait_event(images_landed)
             pc = prepare_captions(captions[c0:c1], ln[c0:c1], device=dev)
             ready = side.record_event()
         main.wait_event(ready)

@@ -331,6 +331,41 @@ def test_cal_sims_and_recall_never_builds_the_matrix():
     assert peak_matrix - peak_fused >= 0.9 * matrix_bytes, (peak_matrix, peak_fused, matrix_bytes)
 
 
+def test_streamed_host_images_give_the_same_results(monkeypatch):
+    """Large host image arrays are uploaded in chunks and scored range by range as they land
+    (ops.prepare_images_streamed): pinned or pageable source, matrix or fused ranking, device or host captions -- the
+    results must be those of one upload + one launch, bit for bit."""
+    monkeypatch.setattr(ops, "STREAMED_IMAGES_MIN_BYTES", 0)
+    n_img, n_cap = 70, 350
+    img, cap, lens = itr_b200.synth.scan_inputs(n_img, n_cap, 10.5, 43, device="cuda")
+    args = ("clipped_l2norm", "LogSumExp", 9.0, 6.0)
+    pc = ops.prepare_captions(cap, lens)
+    want = ops.scan_t2i_scores_bf16(ops.prepare_images(img), pc, *args)
+    want_ranks = sharding.sharded_ranks(want, 0, n_cap, None, 5)
+    pinned = torch.empty(img.shape, dtype=torch.float32, pin_memory=True).copy_(img)
+    pageable = img.cpu().numpy().copy()
+    cap_pinned = torch.empty(cap.shape, dtype=torch.float32, pin_memory=True).copy_(cap)
+    for src in (pinned, pageable):
+        for chunks in (3, 8):
+            pi = ops.prepare_images_streamed(src, "cuda", chunks=chunks)
+            ranges = pi.row_ranges()
+            assert len(ranges) >= 3 and ranges[0][0] == 0 and ranges[-1][1] == n_img and all(lo % 4 == 0 for lo, _, _ in ranges)
+            assert torch.equal(ops.scan_t2i_scores_bf16(pi, pc, *args), want)
+            assert pi.pending is None and pi.row_ranges() == [(0, n_img, False)]       # every range has been waited for
+            # captions streaming from pinned host memory in three chunks at the same time
+            pi = ops.prepare_images_streamed(src, "cuda", chunks=chunks)
+            got = ops.scan_t2i_scores_from_host(pi, cap_pinned, lens, *args, chunks=[(0, 60), (60, 200), (200, n_cap)])
+            assert torch.equal(got, want)
+            # fused ranking: pre-pass on all rows, counting range by range with column accumulation
+            stats = sharding.FusedScanStats(ops.prepare_images_streamed(src, "cuda", chunks=chunks), pc, *args)
+            got_ranks = sharding.sharded_ranks(stats.block(), 0, n_cap, None, 5, stats)
+            assert all(torch.equal(a, b) for a, b in zip(got_ranks, want_ranks))
+    # small arrays and device arrays are not streamed
+    monkeypatch.setattr(ops, "STREAMED_IMAGES_MIN_BYTES", 1 << 40)
+    assert ops.prepare_images_streamed(pinned, "cuda").pending is None
+    assert ops.prepare_images_streamed(img, "cuda", chunks=4).pending is None
+
+
 def test_image_row_ranges_give_the_same_results():
     """The multi-GPU path scores its own image rows before the other ranks' rows have arrived (PreparedImages.row_ranges):
     launching the kernels per row range -- scores, ground-truth pre-pass on the local rows only, counting with column
