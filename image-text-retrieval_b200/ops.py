@@ -276,7 +276,11 @@ class PreparedImages:
         """[(lo, hi, token)] in the order the rows become valid (this rank's own rows first, uploaded chunks in upload
         order); pass the token to wait_rows() before launching on the range."""
         if self.pending:
-            return list(self.pending)
+            rest = []
+            if self.gathered is not None and self.local_rows is not None:
+                lo, hi = self.local_rows
+                rest = [(a, b, True) for a, b in ((0, lo), (hi, self.n_img)) if b > a]
+            return list(self.pending) + rest
         if self.gathered is None or self.local_rows is None:
             return [(0, self.n_img, self.gathered is not None)]
         lo, hi = self.local_rows
@@ -290,6 +294,14 @@ class PreparedImages:
             self.wait_gathered()
         elif token is not None and token is not False:
             torch.cuda.current_stream(self.images_bf16.device).wait_event(token)
+
+    def wait_local(self):
+        """Make the current stream wait for the uploaded chunks only (multi-GPU: this rank's own rows), not for the gather."""
+        if self.pending:
+            stream = torch.cuda.current_stream(self.images_bf16.device)
+            for _, _, ev in self.pending:
+                stream.wait_event(ev)
+        self.pending = None
 
     def ranges_consumed(self):
         """Every entry of row_ranges() has been waited for on the current stream: from now on all rows are valid there."""
@@ -397,6 +409,7 @@ def prepare_images(images, out=None, gram=None) -> PreparedImages:
 
 
 STREAMED_IMAGES_MIN_BYTES = 128 << 20
+STREAMED_SHARD_MIN_BYTES = 48 << 20       # multi-GPU: a rank's own slice of the images
 STREAMED_IMAGE_CHUNKS = 8
 _UPLOAD_STREAMS = {}
 
@@ -516,14 +529,18 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
         sl = torch.from_numpy(np.ascontiguousarray(sl))
     if sl.dtype != torch.float32:
         sl = sl.float()
-    if not sl.is_cuda and not sl.is_pinned() and sl.numel() * 4 >= STAGED_UPLOAD_MIN_BYTES:
-        sl = upload_pageable(sl.contiguous(), dev)
-    else:
-        sl = sl.to(dev, non_blocking=True)
     img_all = torch.empty(world * per, capi.REGIONS, capi.EMBED, device=dev, dtype=torch.bfloat16)
     gram_all = torch.empty(world * per, capi.GRAM_BYTES, device=dev, dtype=torch.uint8)
     img_bytes, gram_bytes = per * capi.REGIONS * capi.EMBED * 2, per * capi.GRAM_BYTES
     ws = _sym_workspace(group, img_bytes + gram_bytes, dev)
+    # a large HOST slice is uploaded in chunks on the upload stream (symmetric-memory path): this rank scores its own rows
+    # chunk by chunk as they land, the peers pull the slice once it is complete
+    streamed = ws is not None and not sl.is_cuda and hi > lo and sl.numel() * 4 >= STREAMED_SHARD_MIN_BYTES
+    if not streamed:
+        if not sl.is_cuda and not sl.is_pinned() and sl.numel() * 4 >= STAGED_UPLOAD_MIN_BYTES:
+            sl = upload_pageable(sl.contiguous(), dev)
+        else:
+            sl = sl.to(dev, non_blocking=True)
     if ws is not None:
         main = torch.cuda.current_stream(dev)
         if ws["done"] is not None:
@@ -531,12 +548,36 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
         mine = ws["buf"]
         sym_img = mine[:img_bytes].view(torch.bfloat16).view(per, capi.REGIONS, capi.EMBED)
         sym_gram = mine[img_bytes: img_bytes + gram_bytes].view(per, capi.GRAM_BYTES)
-        if hi > lo:
-            prepare_images(sl, out=sym_img[: hi - lo], gram=sym_gram[: hi - lo])
-            img_all[lo:hi].copy_(sym_img[: hi - lo])
-            gram_all[lo:hi].copy_(sym_gram[: hi - lo])
+        pending = None
         side = _gather_stream(dev)
-        side.wait_stream(main)
+        if streamed:
+            sl = sl.contiguous()
+            up = _upload_stream(dev)
+            up.wait_stream(main)
+            n_loc = hi - lo
+            step_rows = max(capi.TILE_IMAGES, -(-n_loc // STREAMED_IMAGE_CHUNKS) // capi.TILE_IMAGES * capi.TILE_IMAGES)
+            step_rows += capi.TILE_IMAGES if step_rows * STREAMED_IMAGE_CHUNKS < n_loc else 0
+            pending = []
+            with torch.cuda.stream(up):
+                for a in range(0, n_loc, step_rows):
+                    b = min(a + step_rows, n_loc)
+                    stage = sl[a:b].to(dev, non_blocking=True) if sl.is_pinned() else upload_pageable(sl[a:b], dev)
+                    prepare_images(stage, out=sym_img[a:b], gram=sym_gram[a:b])
+                    img_all[lo + a: lo + b].copy_(sym_img[a:b])
+                    gram_all[lo + a: lo + b].copy_(sym_gram[a:b])
+                    ev = torch.cuda.Event()
+                    ev.record(up)
+                    pending.append((lo + a, lo + b, ev))
+            for x in (img_all, gram_all):
+                x.record_stream(up)
+            side.wait_stream(main)
+            side.wait_event(pending[-1][2])
+        else:
+            if hi > lo:
+                prepare_images(sl, out=sym_img[: hi - lo], gram=sym_gram[: hi - lo])
+                img_all[lo:hi].copy_(sym_img[: hi - lo])
+                gram_all[lo:hi].copy_(sym_gram[: hi - lo])
+            side.wait_stream(main)
         with torch.cuda.stream(side):
             hdl = ws["hdl"]
             hdl.barrier()                                   # every rank's slice is written
@@ -555,7 +596,7 @@ def prepare_images_sharded(images, group=None, device=None) -> PreparedImages:
         ws["done"] = done
         for t in (img_all, gram_all):
             t.record_stream(side)
-        return PreparedImages(img_all[:n_img], gram_all[:n_img], n_img, local_rows=(lo, hi), gathered=done)
+        return PreparedImages(img_all[:n_img], gram_all[:n_img], n_img, local_rows=(lo, hi), gathered=done, pending=pending)
     img_loc = img_all[rank * per:(rank + 1) * per]          # all_gather_into_tensor gathers in place
     gram_loc = gram_all[rank * per:(rank + 1) * per]
     if hi > lo:

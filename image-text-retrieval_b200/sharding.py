@@ -78,6 +78,7 @@ class FusedScanStats:
             lo, hi = pi.local_rows
             g_lo, g_hi = cap_offset // caps_per_img, min(-(-(cap_offset + n_local) // caps_per_img), pi.n_img)
             if n_local > 0 and lo <= g_lo and g_hi <= hi and cap_offset - lo * caps_per_img >= 0:
+                pi.wait_local()               # this rank's own rows may still be arriving in chunks from the host
                 tr, tc = ops.scan_t2i_gt_thresholds(pi.rows(lo, hi), self.pc, *self.args,
                                                     cap_offset=cap_offset - lo * caps_per_img, caps_per_img=caps_per_img)
                 thr_row = torch.full((pi.n_img,), float("-inf"), device=tr.device)
