@@ -54,7 +54,7 @@ constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_AUX = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_ES = SMEM_AUX + 2 * AUX_BYTES;
 constexpr int SMEM_TS = SMEM_ES + NUM_EPI_WARPS * WARP_SCRATCH;
-constexpr int SMEM_BARS = SMEM_TS + NUM_EPI_WARPS * WARP_SCRATCH + 64;      // + slack: fragment reads of padding rows run 48 bytes past a scratch
+constexpr int SMEM_BARS = SMEM_TS + NUM_EPI_WARPS * WARP_SCRATCH;
 constexpr int NUM_BARS = 2 * STAGES + 8;
 constexpr int SMEM_TMEMPTR = SMEM_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = SMEM_TMEMPTR + 16;
@@ -275,6 +275,7 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       // flight lets the refill overtake them (seen as rare stale rows).  The vote consumes every lane's value, and the
       // arrive depends on its result (lane 31 always ends a caption or is padding, so the mask is never 0).
       const uint32_t endmask = __ballot_sync(0xffffffffu, lane == seg_hi);
+      __syncwarp();                                            // orders every lane's read before lane 0's release
       if (lane == 0 && endmask != 0u) mbar_arrive(aempty_bar(b));
       const bool long_tile = (meta.z >> 16) & 1;
       const int img = n * IMGS + g;
@@ -361,8 +362,8 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
 #pragma unroll 1
         for (int mt = 0; mt < 3; ++mt) {
           // A fragments of e^T: a0 = e[8s+2a][16mt+g], a1 = e[8s+2a][16mt+g+8], a2, a3 = the same of word 8s+2a+1; rows 36..47 are
-          // padding (a1 = a3 = 0 in the last tile; its a0/a2 of g >= 4 read finite neighbours and feed rows nobody uses)
-          const uint32_t fo = (uint32_t)(2 * fa) * ROW_BYTES + 4u * (uint32_t)(16 * mt + fg);
+          // padding (a1 = a3 = 0 in the last tile; its a0/a2 of g >= 4 re-read region 35 and feed rows nobody uses)
+          const uint32_t fo = (uint32_t)(2 * fa) * ROW_BYTES + 4u * (uint32_t)min(16 * mt + fg, R - 1);
           float4 ea[4];
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
