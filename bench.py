@@ -348,7 +348,14 @@ def run_side_config(args):
         if direction == "t2i":
             out.update(device_ms_fp32_mode=tot_ms32)
         else:
-            out.update(device_ms_two_phase=tot_ms2p)
+            # affinity flops of the five folds (2 x regions x words x 1024 each) over the whole fold time: the per-caption
+            # contractions on mma.sync and everything else in the fold count as overhead
+            pk = peaks()
+            flop = 2.0 * 36 * 1024 * sum(sh["n_img"] * int(lens_all[sh["fold"] * 5000:(sh["fold"] + 1) * 5000].sum()) for sh in shapes)
+            out.update(device_ms_two_phase=tot_ms2p,
+                       roofline={"bound": "tensor", "achieved": flop / (tot_ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                                 "frac": flop / (tot_ms * 1e-3) / 1e12 / pk["tflops"], "peak_source": pk["src"],
+                                 "scope": "whole fold (prep, Gram fragments, fused kernel, two-phase path of the captions > 32 words, ranking)"})
     print(json.dumps(out), flush=True)
 
 

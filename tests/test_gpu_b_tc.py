@@ -331,6 +331,23 @@ def test_cal_sims_and_recall_never_builds_the_matrix():
     assert peak_matrix - peak_fused >= 0.9 * matrix_bytes, (peak_matrix, peak_fused, matrix_bytes)
 
 
+@pytest.mark.parametrize("agg", ["LogSumExp", "Max"])
+def test_fused_i2t_many_tiny_captions(agg):
+    """Captions of 1..3 words pack 11 to 32 to a 32-row quarter: the fused i2t kernel then walks several caption n-tiles
+    of eight per quarter (its `ct` loop) -- against the two-phase path and the float64 oracle."""
+    n_img, n_cap = 21, 300
+    lens = (np.arange(n_cap) % 3 + 1).astype(np.int32)
+    lens[:40] = 1                                     # a few quarters of 32 single-word captions
+    img, cap, lens = itr_b200.synth.scan_inputs(n_img, n_cap, 2.0, 77, device="cuda", lengths=lens, round_to="bf16")
+    got = ops.scan_i2t_scores_tc(img, cap, lens, "l2norm", agg, 4.0, 6.0)
+    two = ops.scan_scores_tc_generic(img, cap, lens, "i2t", "l2norm", agg, 4.0, 6.0)
+    assert torch.isfinite(got).all()
+    assert ((got - two).abs() / two.abs().clamp_min(1e-6)).max().item() < 2e-3
+    want = so.scan_scores(img.cpu().numpy(), cap.cpu().numpy(), lens, "i2t", "l2norm", agg, 4.0, 6.0)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL_TC, atol=ATOL_TC)
+    assert torch.equal(got, ops.scan_i2t_scores_tc(img, cap, lens, "l2norm", agg, 4.0, 6.0))
+
+
 def test_streamed_host_images_give_the_same_results(monkeypatch):
     """Large host image arrays are uploaded in chunks and scored range by range as they land
     (ops.prepare_images_streamed): pinned or pageable source, matrix or fused ranking, device or host captions -- the
