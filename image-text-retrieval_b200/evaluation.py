@@ -280,6 +280,16 @@ class _ValLogger(dict):
         pass
 
 
+def _host_zeros(shape, pin):
+    """Zeroed float32 host tensor, page-locked if asked for and if the host grants it."""
+    if pin:
+        try:
+            return torch.zeros(shape, dtype=torch.float32, pin_memory=True)
+        except RuntimeError:
+            pass
+    return torch.zeros(shape, dtype=torch.float32)
+
+
 def encode_data(model, data_loader, islength=False):
     """evaluation.py:75-121 with the device->host hand-off changed: embeddings are
     collected in PINNED host buffers and returned as numpy views of them, so every caller keeps working
@@ -292,7 +302,9 @@ def encode_data(model, data_loader, islength=False):
     except Exception:
         val_logger = _ValLogger()
     model.val_start()
-    pin = torch.cuda.is_available()
+    # page-locked result buffers let cal_sims gather / stream them over PCIe; ITR_B200_PIN_EMBEDDINGS=0 keeps them pageable
+    # (as the reference's numpy arrays are), and an allocation the host refuses falls back to pageable memory
+    pin = torch.cuda.is_available() and os.environ.get("ITR_B200_PIN_EMBEDDINGS", "1") != "0"
     n = len(data_loader.dataset)
     max_n_word = 0
     if islength:
@@ -310,11 +322,11 @@ def encode_data(model, data_loader, islength=False):
             cap_size = [n] + list(cap_emb.shape[1:])
             if islength:
                 cap_size[1] = max_n_word
-            img_embs = torch.zeros([n] + list(img_emb.shape[1:]), dtype=torch.float32, pin_memory=pin)
-            cap_embs = torch.zeros(cap_size, dtype=torch.float32, pin_memory=pin)
+            img_embs = _host_zeros([n] + list(img_emb.shape[1:]), pin)
+            cap_embs = _host_zeros(cap_size, pin)
             cap_lens = np.zeros(n, dtype=np.int32)
         if cap_emb.dim() == 3 and cap_emb.size(1) > cap_embs.size(1):          # a later, longer batch (defect D8)
-            grown = torch.zeros([n, cap_emb.size(1)] + list(cap_embs.shape[2:]), dtype=torch.float32, pin_memory=pin)
+            grown = _host_zeros([n, cap_emb.size(1)] + list(cap_embs.shape[2:]), pin)
             grown[:, : cap_embs.size(1)] = cap_embs
             cap_embs = grown
         idx = torch.as_tensor(np.asarray(ids), dtype=torch.long)
@@ -436,17 +448,20 @@ def cal_sims_and_recall(model, img_embs, cap_embs, lengths=None, shard_size=128,
 def cal_sims_and_recall_ensemble(models, img_embs_list, cap_embs_list, lengths_list=None, shard_size=128,
                                  return_sims=False, verbose=False):
     """Two-model (or n-model) ensemble of ``evalrank_ensemble`` (evaluation.py:378-401): the models' score matrices are
-    averaged and ranked on the device, (s1 + s2) / 2 in float32 exactly as the reference's numpy average of the
-    float32 blocks; nothing but the rank vectors comes back."""
+    averaged and ranked on the device.  The reference averages float64 matrices holding float32 values
+    (``(sims + sims_2) / 2``), which is exact; so is the float64 accumulation here (a float32 average could round and
+    create ties or rank flips the reference does not have).  Nothing but the rank vectors comes back."""
     if not (len(models) == len(img_embs_list) == len(cap_embs_list)) or not models:
         raise ValueError("models, img_embs_list and cap_embs_list must be equally long and non-empty")
     lengths_list = lengths_list if lengths_list is not None else [None] * len(models)
     sims = None
     for model, img, cap, ln in zip(models, img_embs_list, cap_embs_list, lengths_list):
         s = device_sims(model, img, cap, ln, shard_size)
+        if len(models) > 1:
+            s = s.double()
         sims = s if sims is None else sims.add_(s)
     if len(models) > 1:
-        sims = sims.mul_(1.0 / len(models))
+        sims = sims.div_(float(len(models)))
     a, b, c, d = [x.cpu().numpy().astype(np.float64) for x in device_ranks(sims)]
     res = _recall_dict(_metrics(a), (a, b), _metrics(c), (c, d), verbose)
     if return_sims:
