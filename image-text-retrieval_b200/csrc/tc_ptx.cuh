@@ -61,19 +61,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {      
     if ((++n & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
   }
 }
-// Watchdog of the sleeping waits: called once every 1024 failed polls (kept out of line so that the clock read and the
-// 64-bit compare do not ride along with every poll); a protocol bug becomes a trap after ~3 s instead of a hang.
-static __device__ __noinline__ void mbar_watchdog(long long t0) {
-  if (clock64() - t0 > 6000000000ll) __trap();
-}
+// The watchdog of the sleeping waits reads the clock once every 1024 failed polls, inline: an out-of-line call here made
+// ptxas spill 27 registers of the counting kernel around the call site (COCO-5K step 134.1 -> 132.8 ms without it).
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {  // throughput warps: sleep
   if (mbar_try_wait(bar, parity)) return;
-  // polls share issue slots with working warps (measured: 13 instructions per failed poll with an inline clock-based
-  // watchdog, ~28 polls per item on the accumulator barrier)
   const long long t0 = clock64();
   int n = 0;
   while (!mbar_try_wait_sleep(bar, parity, 20000u)) {
-    if ((++n & 1023) == 0) mbar_watchdog(t0);
+    if ((++n & 1023) == 0 && clock64() - t0 > 6000000000ll) __trap();
   }
 }
 // wait and add the cycles spent waiting to `acc` (profiling builds of the role loops)
