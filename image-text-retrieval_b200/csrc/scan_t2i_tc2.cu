@@ -320,7 +320,9 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
           }
         }
         const float Qf = c.D + (q0 + q1);
-        const float rj = c.P / fmaxf(c.wnorm * sqrtf(fmaxf(Qf, 0.f)), 1e-8f * Zsum);
+        float sq;                                   // approximate sqrt / division: 2^-22 relative, far inside the bf16 contract
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(Qf, 0.f)));
+        const float rj = __fdividef(c.P, fmaxf(c.wnorm * sq, 1e-8f * Zsum));
         bool pr[5];
 #pragma unroll
         for (int s = 0; s < 5; ++s) pr[s] = (lane - (1 << s)) >= seg_lo;
@@ -339,7 +341,7 @@ scan_t2i_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
           tot = (p.agg == ITR_AGG_MAX) ? fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) : (t0 + t1) + (t2 + t3);
         }
         if (p.agg == ITR_AGG_LSE) tot = lg2f(tot) * p.inv_lse;
-        if (p.agg == ITR_AGG_MEAN) tot = tot / (float)c.n_words;
+        if (p.agg == ITR_AGG_MEAN) tot = __fdividef(tot, (float)c.n_words);
         const bool writer = long_tile ? (row == 0) : (lane == seg_lo);
         if (writer && c.cap >= 0) {
           if (MODE == MODE_SCORES) {
