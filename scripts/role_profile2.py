@@ -29,3 +29,10 @@ items = c[:, 0, 5].mean()
 print("=== pair kernel %d x %d: %.3f ms, item pairs per cluster %.1f" % (n_img, n_cap, ev0.elapsed_time(ev1), items))
 for r, who in enumerate(("leader", "peer")):
     print("  %-6s " % who + "  ".join("%s %.0f" % (nm.replace(" ", "_"), c[:, r, i].mean() / items) for i, nm in enumerate(names) if i != 5))
+# spread across the 74 clusters: with a static schedule the launch ends with the slowest cluster
+for r, who in enumerate(("leader", "peer")):
+    tot, it = c[:, r, 14], c[:, r, 5]
+    print("  %-6s epilogue loop clk per cluster: min %.4g  mean %.4g  max %.4g  (max/mean - 1 = %.2f %%);  items min %d max %d;  clk/item min %.0f max %.0f"
+          % (who, tot.min(), tot.mean(), tot.max(), 100 * (tot.max() / tot.mean() - 1), it.min(), it.max(), (tot / it).min(), (tot / it).max()))
+order = np.argsort(c[:, 0, 14])
+print("  slowest clusters:", order[-6:].tolist(), " fastest:", order[:6].tolist())
