@@ -322,14 +322,6 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
       // streamed from L1/L2 once per row tile (holding it would cost 32 registers)
       const float4* gf = reinterpret_cast<const float4*>(p.gq_frag) + ((size_t)(m * 4 + q) * 8) * 32 + lane;
       const float* vp = p.vnorm + (size_t)img * R + fg;          // |v_k| of this lane's accumulator rows: regions 16 mt + 8 h + g
-      // the Gram is block-diagonal by caption: its 8x8 block (s, nt) is non-zero only if one caption reaches from word group
-      // s into word group nt, i.e. no segment ends between the last word of the lower group and the first of the upper
-      uint32_t gblocks = 0x8421u;                                // the diagonal blocks
-#pragma unroll
-      for (int lo = 0; lo < 3; ++lo)
-#pragma unroll
-        for (int hi = lo + 1; hi < 4; ++hi)
-          if (((endmask >> (8 * lo + 7)) & ((1u << (8 * (hi - lo) - 7)) - 1u)) == 0u) gblocks |= (1u << (4 * lo + hi)) | (1u << (4 * hi + lo));
       const int my_ord = __popc(endv & ((1u << lane) - 1u));      // meaningful on the lanes that end a caption
       const int n_ct = (__popc(endv) + 7) >> 3;                  // caption n-tiles of eight: one unless the captions are tiny
       __syncwarp();
@@ -379,10 +371,11 @@ scan_i2t_tc2_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             const float4 g01 = __ldg(gf + (2 * s) * 32), g23 = __ldg(gf + (2 * s + 1) * 32);
-            if (gblocks & (1u << (4 * s + 0))) mma_tf32(u[0], ea[s], g01.x, g01.y);
-            if (gblocks & (1u << (4 * s + 1))) mma_tf32(u[1], ea[s], g01.z, g01.w);
-            if (gblocks & (1u << (4 * s + 2))) mma_tf32(u[2], ea[s], g23.x, g23.y);
-            if (gblocks & (1u << (4 * s + 3))) mma_tf32(u[3], ea[s], g23.z, g23.w);
+            // (the all-zero 8x8 blocks of the block-diagonal Gram are not skipped: a branch per MMA cost more than it saved)
+            mma_tf32(u[0], ea[s], g01.x, g01.y);
+            mma_tf32(u[1], ea[s], g01.z, g01.w);
+            mma_tf32(u[2], ea[s], g23.x, g23.y);
+            mma_tf32(u[3], ea[s], g23.z, g23.w);
           }
           // hi and lo parts accumulate separately: independent chains of four MMAs instead of one of eight
           float zq[4] = {0.f, 0.f, 0.f, 0.f}, qq[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
