@@ -14,6 +14,14 @@ for r in rows[1:]:
     v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ui].strip().replace("usecond", "us").replace("nsecond", "ns").replace("msecond", "ms"), 1e-6)
     launches.append((r[ki], v))
 starts = [i for i, (k, _) in enumerate(launches) if "prep_images_kernel" in k]
+# an end-to-end step prepares the images in several uploaded chunks (one prep launch each): a new step starts only at a
+# prep launch that follows a score kernel (or is the first)
+merged, seen_score = [], True
+for a, b in zip(starts, starts[1:] + [len(launches)]):
+    if seen_score:
+        merged.append(a)
+    seen_score = any("scan_t2i_tc" in k for k, _ in launches[a:b])
+starts = merged
 print("ncu --metrics gpu__time_duration.sum --clock-control none   command: python bench.py --steps 2 --warmup 1 --no-cpu-baseline")
 print("(per-launch times are cold-cache and serialised: compare SHARES with bench.py's kernel_share_of_step, not absolutes)")
 print("{} launches captured, {} steps (a step starts at prep_images_kernel); launches before the first step are input generation".format(len(launches), len(starts)))
