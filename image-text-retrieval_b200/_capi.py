@@ -58,6 +58,7 @@ SIGNATURES = {
     "itr_rank_thresholds_f32": (_i, [_p, _l, _i, _i, _i, _i, _p, _p, _p]),
     "itr_rank_count_f32": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "itr_rank_f64": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "itr_scores_to_host_f64": (_i, [_p, _l, _i, _i, _p, _l, _p]),
 }
 
 _lib = None

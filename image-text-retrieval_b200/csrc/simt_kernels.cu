@@ -1143,6 +1143,36 @@ extern "C" int itr_multiview_backward_f32(const float* imgs, const float* caps, 
   return ITR_OK;
 }
 
+// Score block -> the host's float64 matrix (evaluation.py:140: cal_sims returns float64), written straight into mapped
+// page-locked host memory over PCIe.  One 128-thread block per SM with a handful of registers: it fits next to the
+// persistent score CTA, so the block of caption chunk k leaves the device while chunk k+1 is being scored.
+__global__ void __launch_bounds__(128, 16)
+scores_to_host_f64_kernel(const float* __restrict__ src, int64_t ld_src, int n_rows, int n_cols, double* __restrict__ dst, int64_t ld_dst) {
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const float* s = src + (int64_t)row * ld_src;
+    double* d = dst + (int64_t)row * ld_dst;
+    int c = threadIdx.x;
+    for (; c + 384 < n_cols; c += 512) {                 // four independent loads in flight per thread
+      const float v0 = s[c], v1 = s[c + 128], v2 = s[c + 256], v3 = s[c + 384];
+      d[c] = (double)v0; d[c + 128] = (double)v1; d[c + 256] = (double)v2; d[c + 384] = (double)v3;
+    }
+    for (; c < n_cols; c += 128) d[c] = (double)s[c];
+  }
+}
+
+extern "C" int itr_scores_to_host_f64(const float* scores, int64_t ld_scores, int n_rows, int n_cols, double* host_mapped,
+                                      int64_t ld_host, void* stream) {
+  ITR_REQUIRE(scores && host_mapped, "itr_scores_to_host_f64: null pointer");
+  ITR_REQUIRE(n_rows >= 0 && n_cols >= 0 && ld_scores >= n_cols && ld_host >= n_cols, "itr_scores_to_host_f64: bad shape");
+  if (n_rows == 0 || n_cols == 0) return ITR_OK;
+  int dev = 0, sms = 0;
+  ITR_CHECK_CUDA(cudaGetDevice(&dev));
+  ITR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  scores_to_host_f64_kernel<<<sms < n_rows ? sms : n_rows, 128, 0, as_stream(stream)>>>(scores, ld_scores, n_rows, n_cols, host_mapped, ld_host);
+  ITR_CHECK_LAUNCH();
+  return ITR_OK;
+}
+
 extern "C" int itr_order_scores_f32(const float* im, const float* s, int n_img, int n_cap, int d, float* scores,
                                     int64_t ld_scores, void* stream) {
   ITR_REQUIRE(im && s && scores, "itr_order_scores_f32: null pointer");

@@ -122,6 +122,62 @@ def _to_host_f64(d):
     return out
 
 
+_D2H_STREAMS = {}
+
+
+class _HostMatrixWriter:
+    """The float64 host matrix of ``cal_sims``, filled block by block while the score kernels are still running: every
+    finished column block is converted and written straight into a page-locked buffer by a small kernel on its own
+    stream (itr_scores_to_host_f64), so only the last, small block's transfer is left when the last kernel ends.  Used
+    when the similarity function reports its blocks (tensor-core SCAN t2i); anything else takes _to_host_f64."""
+
+    def __init__(self, n_img, n_cap):
+        self.shape, self.buf, self.host, self.done, self.stream = (n_img, n_cap), None, None, 0, None
+
+    def block(self, matrix, c0, c1):
+        if os.environ.get("ITR_B200_HOST_MATRIX", "") == "oneshot":      # A/B switch: convert and copy the whole matrix at the end
+            self.done = -1
+            return
+        if self.done != c0 or tuple(matrix.shape) != self.shape or matrix.dtype != torch.float32:
+            self.done = -1                               # not the contiguous left-to-right sequence this writer expects
+            return
+        if self.buf is None:
+            n = matrix.numel()
+            self.buf = _POOL.take(n * 8) if n else None
+            if self.buf is None:
+                self.done = -1
+                return
+            self.host = self.buf[: n * 8].view(torch.float64).view(self.shape)
+            dev = matrix.device
+            key = dev.index if dev.index is not None else torch.cuda.current_device()
+            if key not in _D2H_STREAMS:
+                _D2H_STREAMS[key] = torch.cuda.Stream(device=dev)
+            self.stream = _D2H_STREAMS[key]
+        ready = torch.cuda.current_stream(matrix.device).record_event()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            ops.scores_to_host_f64(matrix[:, c0:c1], self.host[:, c0:c1])
+        self.done = c1
+
+    def finish(self, matrix):
+        """The finished read-only ndarray, or None when the blocks did not cover the matrix (the caller converts it whole)."""
+        if self.buf is None or self.done != self.shape[1] or self.done < 0:
+            if self.buf is not None:
+                if self.stream is not None:
+                    self.stream.synchronize()
+                _release_pinned(self.buf)
+            return None
+        matrix.record_stream(self.stream)
+        self.stream.synchronize()
+        n = self.shape[0] * self.shape[1]
+        root = self.buf.numpy()
+        weakref.finalize(root, _release_pinned, self.buf)
+        out = root[: n * 8].view(np.float64).reshape(self.shape)
+        del root
+        out.setflags(write=False)
+        return out
+
+
 def _device():
     if not torch.cuda.is_available():
         raise RuntimeError("itr_b200 needs a CUDA device; there is no CPU fallback")
@@ -151,13 +207,17 @@ def _effective_lengths(lengths, n_cap, shard_size, compat_unsliced_lengths):
     return ln
 
 
-def _scan_t2i_from(pi, caps, ln, norm, config, dev):
+def _scan_t2i_from(pi, caps, ln, norm, config, dev, on_block=None):
     """Fused t2i scores from prepared images and captions that are either on the device or in pinned host memory
-    (gathered in place over PCIe, pipelined against the score kernel)."""
+    (gathered in place over PCIe, pipelined against the score kernel).  on_block(matrix, c0, c1) is called after the
+    launch that completes columns [c0, c1) (cal_sims ships them to the host meanwhile)."""
     args = (norm, config["agg_func"], config["lambda_softmax"], config.get("lambda_lse", 6.0))
     if not caps.is_cuda:
-        return ops.scan_t2i_scores_from_host(pi, caps, ln, *args, device=dev)
-    return ops.scan_t2i_scores_bf16(pi, ops.prepare_captions(caps, ln, device=dev), *args)
+        return ops.scan_t2i_scores_from_host(pi, caps, ln, *args, device=dev, on_block=on_block)
+    out = ops.scan_t2i_scores_bf16(pi, ops.prepare_captions(caps, ln, device=dev), *args)
+    if on_block is not None:
+        on_block(out, 0, out.size(1))
+    return out
 
 
 def _sim_function(model):
@@ -201,7 +261,7 @@ def _tc_t2i_inputs(model, img_embs, cap_embs, ln, image_group, dev):
 
 
 def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_unsliced_lengths=False,
-                image_group=None):
+                image_group=None, on_block=None):
     """The score matrix as a CUDA float32 tensor (n_img, n_cap); inputs host or device.
     image_group: torch.distributed group over which the image preparation is sharded and all-gathered
     (tensor-core SCAN path only; every rank passes the full image array and its own captions)."""
@@ -219,7 +279,7 @@ def device_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_
                 pi, caps, norm = tc
                 if n_cap == 0:
                     return torch.empty(n_img, 0, device=dev, dtype=torch.float32)
-                return _scan_t2i_from(pi, caps, ln, norm, config, dev)
+                return _scan_t2i_from(pi, caps, ln, norm, config, dev, on_block)
             img = _to_device(img_embs, dev)
             if cal_fun is objectives.cosine_sim:
                 return ops.cosine_scores(img, _to_device(cap_embs, dev))
@@ -348,8 +408,11 @@ def cal_sims(model, img_embs, cap_embs, lengths=None, shard_size=128, compat_uns
     uploading the matrix again.  Anything derived from it (a copy, an average of two matrices) is ranked from the
     host values as before."""
     t0 = time.time()
-    d = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths)
-    out = _to_host_f64(d)
+    ship = _HostMatrixWriter(len(img_embs), len(cap_embs))
+    d = device_sims(model, img_embs, cap_embs, lengths, shard_size, compat_unsliced_lengths, on_block=ship.block)
+    out = ship.finish(d)
+    if out is None:
+        out = _to_host_f64(d)
     if out.size:
         _remember(out, d)
     print("Calculate similarity matrix elapses: {:.3f}s".format(time.time() - t0))

@@ -260,6 +260,13 @@ int itr_rank_count_f32(const float* scores, int64_t ld_scores, int n_img, int n_
                        const float* thr_row, const float* thr_col,
                        int32_t* cnt_row, int32_t* cnt_col, uint64_t* best_row, uint64_t* best_col, void* stream);
 
+/* cal_sims hands back a host float64 matrix (evaluation.py:140,152): converts a device float32 score block and writes it
+ * straight into MAPPED page-locked host memory (cudaHostAlloc / pinned torch memory; row pitch ld_host in elements).  A
+ * 128-thread block per SM: runs next to the persistent score kernel, so finished caption blocks leave the device while
+ * the next ones are scored. */
+int itr_scores_to_host_f64(const float* scores, int64_t ld_scores, int n_rows, int n_cols, double* host_mapped,
+                           int64_t ld_host, void* stream);
+
 /* float64 variant for a whole host-provided matrix (i2t(sims) / t2i(sims) take the float64
  * array cal_sims returns, evaluation.py:140,156,192): ranks (strictly-greater counts) and the
  * arg-max (lowest index on ties) of every row and every column. */

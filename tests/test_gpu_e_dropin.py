@@ -111,6 +111,30 @@ def test_cal_recall_reuses_the_device_matrix(name):
     assert all(e.ref() is not None for e in ev._SIMS.values())
 
 
+def test_cal_sims_ships_blocks_while_scoring():
+    """cal_sims fills its float64 host matrix block by block while the later caption chunks are still being scored
+    (evaluation._HostMatrixWriter + itr_scores_to_host_f64): the result must be the one-shot conversion of the device
+    matrix, bit for bit -- for captions streaming from pinned memory in several chunks, for device captions (one block)
+    and for a similarity function that reports no blocks at all."""
+    model = FakeModel(cfg())
+    img, cap, lens = itr_b200.synth.scan_inputs(220, 1100, 10.5, 6)        # > 8192 words: several caption chunks
+    assert len(ops.host_caption_chunks(np.asarray(lens), fractions=(3.0 / 16, 5.0 / 16, 1.0 / 4, 1.0 / 8, 1.0 / 8))) == 5
+    cap_pinned = torch.empty(cap.shape, dtype=torch.float32, pin_memory=True).copy_(cap)
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = ev.cal_sims(model, img.numpy(), cap_pinned.numpy(), lens)
+        got_dev_caps = ev.cal_sims(model, img.numpy(), cap.numpy().copy(), lens)      # pageable captions: uploaded whole, one block
+    want = ev.device_sims(model, img.numpy(), cap.numpy(), lens).double().cpu().numpy()
+    assert got.dtype == np.float64 and got.flags.c_contiguous and not got.flags.writeable
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got_dev_caps, want)
+    res = ev.cal_recall(got)                                                       # still ranked from the device twin
+    assert res["rsum"] == pytest.approx(so.recall_dict(want)["rsum"])
+    vse = FakeModel(cfg(name="VSE++"))
+    im, s = itr_b200.synth.vse_inputs(40, 200, 9)
+    with contextlib.redirect_stdout(io.StringIO()):
+        np.testing.assert_array_equal(ev.cal_sims(vse, im, s), ev.device_sims(vse, im, s).double().cpu().numpy())
+
+
 def test_pinned_pool_recycles_and_isolates():
     """Two live matrices never share a buffer; a dead one's buffer is reused."""
     model = FakeModel(cfg(name="VSE++"))
