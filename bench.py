@@ -125,7 +125,7 @@ class ClockSampler:
 
 
 _CPU_INPUTS = {}
-CPU_SAMPLE = (1000, 100)      # images x captions of the COCO-5K-shaped workload scored per CPU step (both CPU legs)
+CPU_SAMPLE = (1000, 700)      # images x captions of the COCO-5K-shaped workload scored per CPU step (both CPU legs): ~11 s on 16 cores
 
 
 def _reference_fns():
@@ -183,6 +183,11 @@ def run_reference(args, rank, world):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     n_img_s, n_cap_s = min(CPU_SAMPLE[0], args.n_img), min(CPU_SAMPLE[1], args.n_cap)
+    # the whole --steps K --warmup W run has to end within a few minutes whatever K is: a 40-caption probe gives the rate,
+    # and the per-step sample shrinks (never below 100 captions) if K + W full samples would take more than ~150 s
+    probe_rate = cpu_reference_rate(n_img_s, min(40, n_cap_s))[0]
+    budget_caps = int(probe_rate * 150.0 / max(1, args.warmup + args.steps) / n_img_s)
+    n_cap_s = max(min(100, n_cap_s), min(n_cap_s, budget_caps // 20 * 20))
     times = []
     for i in range(args.warmup + args.steps):
         rate, secs, cores, kind = cpu_reference_rate(n_img_s, n_cap_s)
