@@ -97,3 +97,40 @@ def test_synth_shapes_and_length_sums():
     assert torch.equal(img, img.to(torch.bfloat16).float())
     im, s = itr_b200.synth.vse_inputs(10, 50, 3, d=32, raw_dim=48)
     assert im.shape == (10, 32) and s.shape == (50, 32)
+
+
+def test_host_caption_chunks_cover_the_captions_in_order():
+    """ops.host_caption_chunks: contiguous ranges on multiples of five that cover every caption once, whatever the
+    fractions (pipelined host path, block-shipped cal_sims matrix); small inputs stay in one piece."""
+    from itr_b200 import ops
+    lens = itr_b200.synth.caption_lengths(4000, 10.5, 3)
+    for fr in ((1.0 / 16, 3.0 / 16, 3.0 / 4), (3.0 / 16, 5.0 / 16, 1.0 / 2), (3.0 / 16, 5.0 / 16, 1.0 / 4, 1.0 / 8, 1.0 / 8)):
+        chunks = ops.host_caption_chunks(lens, fractions=fr)
+        assert len(chunks) == len(fr)
+        assert chunks[0][0] == 0 and chunks[-1][1] == len(lens)
+        assert all(a[1] == b[0] for a, b in zip(chunks, chunks[1:])) and all(c1 > c0 and c0 % 5 == 0 for c0, c1 in chunks)
+        words = [int(lens[c0:c1].sum()) for c0, c1 in chunks]
+        assert abs(words[0] / float(lens.sum()) - fr[0]) < 0.01
+    assert ops.host_caption_chunks(lens[:100]) == [(0, 100)]
+    assert ops.host_caption_chunks(lens[:0]) == [(0, 0)]
+
+
+def test_prepared_images_row_ranges_order():
+    """PreparedImages.row_ranges: uploaded chunks first (in upload order, each with its event), then the rows that wait for
+    the other ranks' slices; once consumed, one range over everything."""
+    import torch
+    from itr_b200 import ops
+    img = torch.zeros(40, 36, 1024, dtype=torch.bfloat16)
+    gram = torch.zeros(40, 8, dtype=torch.uint8)
+    pi = ops.PreparedImages(img, gram, 40)
+    assert pi.row_ranges() == [(0, 40, False)]
+    pi = ops.PreparedImages(img, gram, 40, local_rows=(8, 16), gathered="gather-event")
+    assert pi.row_ranges() == [(8, 16, False), (0, 8, True), (16, 40, True)]
+    pi = ops.PreparedImages(img, gram, 40, local_rows=(8, 16), gathered="gather-event", pending=[(8, 12, "e0"), (12, 16, "e1")])
+    assert pi.row_ranges() == [(8, 12, "e0"), (12, 16, "e1"), (0, 8, True), (16, 40, True)]
+    pi.ranges_consumed()
+    assert pi.pending is None and pi.row_ranges() == [(8, 16, False), (0, 8, True), (16, 40, True)]
+    pi = ops.PreparedImages(img, gram, 40, pending=[(0, 20, "e0"), (20, 40, "e1")])
+    assert [r[:2] for r in pi.row_ranges()] == [(0, 20), (20, 40)]
+    pi.ranges_consumed()
+    assert pi.row_ranges() == [(0, 40, False)]
